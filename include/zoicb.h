@@ -1,0 +1,172 @@
+/* zoicb.h -- C ABI of libzoicb: batched, B200-native (sm_100a) camera-ray generation with the
+ * behaviour of the zoic Arnold camera's camera_create_ray.
+ *
+ * This is the drop-in boundary.  Plain C types only: no C++ objects, no torch
+ * types, no exceptions across the boundary.  Every entry point returns a zoicb_status; the text of
+ * the last error of the calling thread is available from zoicb_last_error().
+ *
+ * What each entry point replaces in the reference (paths relative to the reference tree):
+ *   zoicb_create        node_initialize + node_update            src/zoic.cpp:1565-1572, 1575-1720
+ *   zoicb_generate      camera_create_ray, one call per BATCH    src/zoic.cpp:1752-1990
+ *   zoicb_generate_host the same, host buffers in / out          src/zoic.cpp:1752-1990
+ *   zoicb_get_stats     the counters printed by node_finish      src/zoic.cpp:1729-1732
+ *   zoicb_destroy       node_finish                              src/zoic.cpp:1723-1749
+ *   zoicb_params        the 14 node parameters                   src/zoic.cpp:1547-1562
+ * The Arnold-shaped per-sample surface (NodeLoader + the six node callbacks, src/zoic.cpp:1999-2007)
+ * is exported by the same library from zoic_b200/csrc/arnold_adapter.cpp on top of these calls.
+ *
+ * There is no CPU fallback: every generate call runs CUDA kernels and fails with
+ * ZOICB_ERR_CUDA when no sm_100 device is usable.
+ */
+#ifndef ZOICB_H
+#define ZOICB_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define ZOICB_API __attribute__((visibility("default")))
+#else
+#define ZOICB_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum zoicb_status {
+    ZOICB_OK = 0,
+    ZOICB_ERR_INVALID_ARGUMENT = 1,
+    ZOICB_ERR_LENS_FILE = 2,      /* cannot open / parse the tabular lens file, bad column count   */
+    ZOICB_ERR_LENS_DATA = 3,      /* more than one aperture stop, too many elements                */
+    ZOICB_ERR_BOKEH_IMAGE = 4,    /* useImage set but no usable pixels (needs >= 3 channels)       */
+    ZOICB_ERR_CUDA = 5,           /* no device, launch failure, allocation failure                 */
+    ZOICB_ERR_UNSUPPORTED = 6
+} zoicb_status;
+
+/* lensModel values (reference enum LensModel, src/zoic.cpp:84-88) */
+enum { ZOICB_THINLENS = 0, ZOICB_RAYTRACED = 1 };
+
+/* Arithmetic mode of the ray kernels.
+ * EXACT   : bit-for-bit the reference's fp32/double arithmetic (no FMA contraction, double where the
+ *           reference promotes).  Identical accept/reject decisions, identical bits.
+ * GUARDED : FMA / reciprocal fast path whose every accept/reject decision carries an error margin; a ray
+ *           that comes within the margin of any threshold is re-run through the EXACT path, so the
+ *           decision sequence (tries, zero weight) equals EXACT and values agree to ~1e-6.  Default. */
+enum { ZOICB_MODE_EXACT = 0, ZOICB_MODE_GUARDED = 1 };
+
+/* The 14 node parameters, same names, meaning, units (cm) and defaults as the reference
+ * (src/zoic.cpp:1547-1562).  Use zoicb_default_params() to get the defaults. */
+typedef struct zoicb_params {
+    float sensorWidth;               /* 3.6   */
+    float sensorHeight;              /* 2.4   */
+    float focalLength;               /* 2.0   */
+    float fStop;                     /* 4.0   */
+    float focalDistance;             /* 100.0 */
+    int32_t useImage;                /* false */
+    int32_t lensModel;               /* ZOICB_RAYTRACED */
+    int32_t kolbSamplingLUT;         /* true  */
+    int32_t useDof;                  /* true  */
+    float opticalVignettingDistance; /* 0.0   */
+    float opticalVignettingRadius;   /* 1.0   */
+    float exposureControl;           /* 0.0   */
+    const char* lensDataPath;        /* ""  : tabular lens description (lenses_tabular/ *.dat grammar) */
+    const char* bokehPath;           /* ""  : label only; pixels are handed to zoicb_create directly  */
+} zoicb_params;
+
+/* Counters (64-bit, exact).  success / vignetted / total_internal_reflection are the reference's
+ * succesRays / vignettedRays / totalInternalReflection (src/zoic.cpp:533-534); attempts and
+ * element_visits feed the roofline flop count; exact_reruns counts rays the GUARDED mode re-ran. */
+typedef struct zoicb_stats {
+    uint64_t rays;
+    uint64_t success;
+    uint64_t vignetted;
+    uint64_t total_internal_reflection;
+    uint64_t attempts;
+    uint64_t element_visits;
+    uint64_t exact_reruns;
+} zoicb_stats;
+
+/* Derived camera state, for parity tests against the reference's setup (src/zoic.cpp:1575-1720). */
+#define ZOICB_MAX_ELEMENTS 24
+#define ZOICB_LUT_SIZE 32
+typedef struct zoicb_constants {
+    int32_t lensCount;
+    int32_t apertureElement;
+    int32_t lutSize;
+    int32_t bokehWidth, bokehHeight;
+    float fov, tan_fov, apertureRadius;                    /* thin lens, :1606-1608 */
+    float userApertureRadius, originShift, apertureDistance, focalLengthRatio;
+    float tracedFocalLength[2], principalPlane[2], focalPoint[2];
+    float curvature[ZOICB_MAX_ELEMENTS], thickness[ZOICB_MAX_ELEMENTS], ior[ZOICB_MAX_ELEMENTS];
+    float aperture[ZOICB_MAX_ELEMENTS], center[ZOICB_MAX_ELEMENTS];
+    float lutKey[ZOICB_LUT_SIZE];
+    float lutMinX[ZOICB_LUT_SIZE], lutMinY[ZOICB_LUT_SIZE], lutMaxX[ZOICB_LUT_SIZE], lutMaxY[ZOICB_LUT_SIZE];
+} zoicb_constants;
+
+typedef struct zoicb_ctx zoicb_ctx;
+
+ZOICB_API void zoicb_default_params(zoicb_params* p);
+
+/* Build a camera on CUDA device `device`: parse params->lensDataPath, run the reference's setup pipeline
+ * bit-exactly on the host (exit-pupil LUT traced on the GPU), build the bokeh row/column CDF tables from
+ * `rgb` (row-major, channel-interleaved, height x width x nch floats; may be NULL unless useImage), and
+ * upload everything.  The context is immutable afterwards, so generate calls are thread-safe. */
+ZOICB_API zoicb_status zoicb_create(const zoicb_params* params, const float* rgb, int width, int height, int nch,
+                          int device, zoicb_ctx** out);
+ZOICB_API void zoicb_destroy(zoicb_ctx* ctx);
+
+ZOICB_API zoicb_status zoicb_set_mode(zoicb_ctx* ctx, int mode);
+ZOICB_API int zoicb_get_mode(const zoicb_ctx* ctx);
+
+/* camera_create_ray for a flat batch.  All pointers are DEVICE pointers owned by the caller:
+ *   d_samples    n x float4 (sx, sy, lensx, lensy)          -- AtCameraInput fields zoic reads
+ *   d_origin_w   n x float4 (origin.x, origin.y, origin.z, weight)
+ *   d_dir_tries  n x float4 (dir.x, dir.y, dir.z, (float)tries)   tries > 0 <=> the reference also sets
+ *                                                            dOdy = origin, dDdy = dir (:1974-1977)
+ * Initial AtCameraOutput state is origin = 0, weight = 1.  Retried samples draw from a per-sample
+ * xorshift128 stream seeded from (rng_seed, first_index + i), so results do not
+ * depend on batch boundaries, launch order or GPU count.  Asynchronous on `stream` (a cudaStream_t). */
+ZOICB_API zoicb_status zoicb_generate(zoicb_ctx* ctx, const void* d_samples, uint64_t n, uint64_t first_index,
+                            uint64_t rng_seed, void* d_origin_w, void* d_dir_tries, void* stream);
+
+/* The same with HOST buffers: pipelines host->device copies, kernels and device->host copies through
+ * pinned staging chunks.  Synchronous. */
+ZOICB_API zoicb_status zoicb_generate_host(zoicb_ctx* ctx, const float* h_samples, uint64_t n, uint64_t first_index,
+                                 uint64_t rng_seed, float* h_origin_w, float* h_dir_tries);
+
+/* Synthetic camera samples for benchmarks and parity tests: sample index i is
+ * pixel-major / spp-minor over a W x H image, four 24-bit uniforms from a counter hash of (seed, i). */
+ZOICB_API zoicb_status zoicb_synth_samples(zoicb_ctx* ctx, uint32_t W, uint32_t H, uint32_t spp, uint64_t seed,
+                                 uint64_t first_index, uint64_t n, void* d_samples, void* stream);
+
+/* Counters accumulate over generate calls; get synchronises the context's device. */
+ZOICB_API zoicb_status zoicb_get_stats(zoicb_ctx* ctx, zoicb_stats* out);
+ZOICB_API zoicb_status zoicb_reset_stats(zoicb_ctx* ctx);
+
+ZOICB_API zoicb_status zoicb_get_constants(const zoicb_ctx* ctx, zoicb_constants* out);
+/* Bokeh tables (each may be NULL): cdfRow[h], rowIndices[h], cdfColumn[w*h], columnIndices[w*h]. */
+ZOICB_API zoicb_status zoicb_get_bokeh_tables(const zoicb_ctx* ctx, float* cdfRow, int32_t* rowIndices,
+                                    float* cdfColumn, int32_t* columnIndices);
+
+/* Host-only setup: runs the whole creation pipeline WITHOUT a device (exit-pupil LUT candidates are
+ * classified by host threads instead of the GPU kernel) and returns the derived constants and, optionally,
+ * the bokeh tables.  For parity tests of the host logic on machines without a GPU; it cannot generate rays. */
+ZOICB_API zoicb_status zoicb_setup_host_only(const zoicb_params* params, const float* rgb, int width, int height, int nch,
+                                   zoicb_constants* out, float* cdfRow, int32_t* rowIndices, float* cdfColumn,
+                                   int32_t* columnIndices);
+
+/* Measured fp32 FMA throughput of the device (dependent-chain-free FFMA kernel), in TFLOP/s: the
+ * denominator of the fp32 roofline that bench.py reports. */
+ZOICB_API zoicb_status zoicb_measure_fp32_peak(int device, double* tflops);
+
+/* Number of kernels this library has launched in the calling process (all contexts). */
+ZOICB_API uint64_t zoicb_kernel_launches(void);
+
+ZOICB_API const char* zoicb_last_error(void);
+ZOICB_API const char* zoicb_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ZOICB_H */

@@ -1,0 +1,149 @@
+"""GPU parity: the CUDA path, called through the C ABI, against the CPU oracle on identical inputs.
+
+EXACT mode must reproduce the oracle BIT FOR BIT (origin, dir, weight, tries and the counters); the
+north-star tolerance (1e-5 relative per vector) is therefore met with zero path flips.
+"""
+import numpy as np
+import pytest
+
+from zutil import bits_equal, compare_rays, random_samples
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+
+def _run_gpu(cam, s, seed, first_index=0):
+    t = torch.from_numpy(s).cuda()
+    cam.reset_stats()
+    o, d = cam.create_rays(t, seed=seed, first_index=first_index)
+    torch.cuda.synchronize()
+    return o.cpu().numpy(), d.cpu().numpy(), cam.stats()
+
+
+def _check_exact(kw, port, n=200_000, seed=11, image=None):
+    from zoic_b200 import ZoicCamera, MODE_EXACT
+    cam = ZoicCamera(image=image, mode=MODE_EXACT, **kw)
+    ref = port.PortCamera(image=image, **kw)
+    s = random_samples(n, seed=seed)
+    o, d, st = _run_gpu(cam, s, seed=seed, first_index=12345)
+    o2, d2, st2 = ref.generate(s, seed=seed, first_index=12345, nthreads=8)
+    res = compare_rays(o, d, o2, d2)
+    assert res["path_flips"] == 0 and res["out_of_tol"] == 0, res
+    # zero-weight rays hold the half-traced state of the last attempt: compare their bits too (same arithmetic)
+    assert bits_equal(o, o2) and bits_equal(d, d2), res
+    assert st["rays"] == n
+    assert st["attempts"] == st2["attempts"]
+    assert st["element_visits"] == st2["element_visits"]
+    assert st["total_internal_reflection"] == st2["tir"]
+    if kw.get("lensModel", 1) == 1 or kw.get("useDof", 1):
+        assert st["success"] == st2["success"] and st["vignetted"] == st2["vignetted"]
+    cam.close()
+    ref.close()
+
+
+def test_thin_lens_plain(port):
+    _check_exact(dict(lensModel=0, focalLength=3.5, fStop=2.8), port)
+
+
+def test_thin_lens_no_dof(port):
+    _check_exact(dict(lensModel=0, focalLength=3.5, fStop=2.8, useDof=0, exposureControl=0.5), port)
+
+
+def test_thin_lens_optical_vignetting(port):
+    _check_exact(dict(lensModel=0, focalLength=3.5, fStop=2.8, opticalVignettingDistance=2.0,
+                      opticalVignettingRadius=1.0, exposureControl=-1.25), port)
+
+
+def test_thin_lens_hex_bokeh(port):
+    from zoic_b200.synth import hex_bokeh_image
+    _check_exact(dict(lensModel=0, focalLength=3.5, fStop=2.8, opticalVignettingDistance=2.0, useImage=1), port,
+                 image=hex_bokeh_image(255))
+
+
+def test_thin_lens_nonsquare_even_bokeh(port):
+    from zoic_b200.synth import hex_bokeh_image
+    img = hex_bokeh_image(33)[:, :20].copy()
+    _check_exact(dict(lensModel=0, focalLength=3.5, fStop=2.8, opticalVignettingDistance=2.0, useImage=1), port,
+                 image=img, n=50_000)
+
+
+@pytest.mark.parametrize("lens", ["double_gauss_f2.0.dat", "fisheye_muller_f4.0.dat", "petzval_f1.6.dat",
+                                  "telephoto_f5.0.dat", "tessar_f2.8.dat", "triplet_f2.5.dat", "mori_f2.8.dat",
+                                  "petzval_f1.25.dat"])
+def test_kolb_lut_all_lenses(port, lens):
+    from zoic_b200.workloads import LENSES, lens_path
+    fnum, focal = LENSES[lens]
+    _check_exact(dict(lensModel=1, lensDataPath=lens_path(lens), focalLength=focal, fStop=fnum), port, n=60_000)
+
+
+def test_kolb_no_lut(port):
+    from zoic_b200.workloads import lens_path
+    _check_exact(dict(lensModel=1, lensDataPath=lens_path("double_gauss_f2.0.dat"), focalLength=5.0, fStop=2.0,
+                      kolbSamplingLUT=0, exposureControl=1.5), port, n=60_000)
+
+
+def test_kolb_lut_hex_bokeh(port):
+    from zoic_b200.synth import hex_bokeh_image
+    from zoic_b200.workloads import lens_path
+    _check_exact(dict(lensModel=1, lensDataPath=lens_path("double_gauss_f2.0.dat"), focalLength=5.0, fStop=2.0,
+                      useImage=1), port, n=60_000, image=hex_bokeh_image(255))
+
+
+def test_synth_samples_match_oracle(port):
+    from zoic_b200 import ZoicCamera
+    cam = ZoicCamera(lensModel=0, focalLength=3.5, fStop=2.8)
+    for (W, H, spp, first, n) in [(1920, 1080, 1, 0, 100_000), (3840, 2160, 256, 2_000_000_000, 100_000),
+                                  (7680, 4320, 1024, 33_973_000_000, 65_536)]:
+        g = cam.synth_samples(W, H, spp, 0x200C, first, n).cpu().numpy()
+        c = port.synth_samples(W, H, spp, 0x200C, first, n)
+        assert bits_equal(g, c)
+    cam.close()
+
+
+def test_batch_boundaries_do_not_matter(port):
+    """Results depend on (seed, global sample index) only: splitting a batch changes nothing."""
+    from zoic_b200 import ZoicCamera, MODE_EXACT
+    from zoic_b200.workloads import lens_path
+    cam = ZoicCamera(mode=MODE_EXACT, lensModel=1, lensDataPath=lens_path("fisheye_muller_f4.0.dat"),
+                     focalLength=1.0, fStop=4.0)
+    s = random_samples(50_000, seed=3)
+    o, d, _ = _run_gpu(cam, s, seed=9, first_index=0)
+    oa, da, _ = _run_gpu(cam, s[:20_001], seed=9, first_index=0)
+    ob, db, _ = _run_gpu(cam, s[20_001:], seed=9, first_index=20_001)
+    assert bits_equal(o, np.concatenate([oa, ob])) and bits_equal(d, np.concatenate([da, db]))
+    cam.close()
+
+
+def test_host_buffer_entry_point(port):
+    from zoic_b200 import ZoicCamera, MODE_EXACT
+    from zoic_b200.workloads import lens_path
+    kw = dict(lensModel=1, lensDataPath=lens_path("double_gauss_f2.0.dat"), focalLength=5.0, fStop=2.0)
+    cam = ZoicCamera(mode=MODE_EXACT, **kw)
+    ref = port.PortCamera(**kw)
+    s = random_samples(300_000, seed=5)
+    o2, d2, _ = ref.generate(s, seed=4, first_index=77, nthreads=8)
+    o, d = cam.create_rays_host(s, seed=4, first_index=77)             # pageable numpy memory
+    assert bits_equal(o, o2) and bits_equal(d, d2)
+    sp = torch.from_numpy(s).pin_memory()
+    op = torch.empty((len(s), 4), dtype=torch.float32).pin_memory()
+    dp = torch.empty((len(s), 4), dtype=torch.float32).pin_memory()
+    cam.create_rays_host(sp, seed=4, first_index=77, out=(op, dp))     # pinned memory, direct DMA
+    assert bits_equal(op.numpy(), o2) and bits_equal(dp.numpy(), d2)
+    cam.close()
+    ref.close()
+
+
+def test_empty_batch_and_errors():
+    from zoic_b200 import ZoicCamera, capi
+    cam = ZoicCamera(lensModel=0, focalLength=3.5, fStop=2.8)
+    t = torch.empty((0, 4), dtype=torch.float32, device="cuda")
+    o, d = cam.create_rays(t)
+    assert o.shape == (0, 4)
+    cam.close()
+    with pytest.raises(capi.ZoicError) as e:
+        ZoicCamera(lensModel=1, lensDataPath="/nonexistent/lens.dat")
+    assert e.value.code == capi.ERR_LENS_FILE
+    with pytest.raises(capi.ZoicError) as e:
+        ZoicCamera(lensModel=0, useImage=1)
+    assert e.value.code == capi.ERR_BOKEH_IMAGE

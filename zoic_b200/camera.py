@@ -1,0 +1,179 @@
+"""Host-side mirror of the reference camera node on top of the C ABI.
+
+`ZoicCamera(**node_parameters)` plays the role of node_initialize + node_update (reference
+src/zoic.cpp:1565-1720); `create_rays` is camera_create_ray (src/zoic.cpp:1752-1990) for a whole batch
+of (sx, sy, lensx, lensy) samples; `stats()` returns the counters node_finish prints (:1729-1732);
+`close()` is node_finish.  Parameter names, units and defaults are the reference's.
+
+torch is used only to own device memory and streams; the data path is libzoicb's CUDA kernels.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+
+THINLENS, RAYTRACED = capi.THINLENS, capi.RAYTRACED
+MODE_EXACT, MODE_GUARDED = capi.MODE_EXACT, capi.MODE_GUARDED
+
+_BOOL_KEYS = ("useImage", "kolbSamplingLUT", "useDof")
+
+
+def make_params(**kw):
+    lib = capi.load()
+    p = capi.Params()
+    lib.zoicb_default_params(C.byref(p))
+    for k, v in kw.items():
+        if not hasattr(p, k):
+            raise TypeError("unknown zoic parameter %r" % k)
+        if k in ("lensDataPath", "bokehPath"):
+            v = v.encode() if isinstance(v, str) else v
+        elif k in _BOOL_KEYS or k == "lensModel":
+            if isinstance(v, str):
+                v = {"THINLENS": THINLENS, "RAYTRACED": RAYTRACED}[v]
+            v = int(v)
+        setattr(p, k, v)
+    return p
+
+
+def _constants_to_dict(c):
+    n, nl = c.lensCount, c.lutSize
+    out = {k: getattr(c, k) for k in ("lensCount", "apertureElement", "lutSize", "bokehWidth", "bokehHeight")}
+    for k in ("fov", "tan_fov", "apertureRadius", "userApertureRadius", "originShift", "apertureDistance",
+              "focalLengthRatio"):
+        out[k] = np.float32(getattr(c, k))
+    for k in ("tracedFocalLength", "principalPlane", "focalPoint"):
+        out[k] = np.array(getattr(c, k), np.float32)
+    out["lenses"] = np.stack([np.array(getattr(c, k), np.float32)[:n]
+                              for k in ("curvature", "thickness", "ior", "aperture", "center")], 1)
+    out["lut"] = np.stack([np.array(getattr(c, k), np.float32)[:nl]
+                           for k in ("lutKey", "lutMinX", "lutMinY", "lutMaxX", "lutMaxY")], 1)
+    return out
+
+
+def host_setup(image=None, **kw):
+    """Run the host-side setup without a GPU (parity tests of the host logic).  Returns (constants, tables)."""
+    lib = capi.load()
+    p = make_params(**kw)
+    img_ptr, w, h, nch = None, 0, 0, 0
+    tabs = [None] * 4
+    ptrs = [None] * 4
+    if image is not None:
+        img = np.ascontiguousarray(image, np.float32)
+        h, w, nch = img.shape
+        img_ptr = img.ctypes.data
+        tabs = [np.zeros(h, np.float32), np.zeros(h, np.int32), np.zeros(h * w, np.float32), np.zeros(h * w, np.int32)]
+        ptrs = [t.ctypes.data for t in tabs]
+    c = capi.Constants()
+    capi.check(lib.zoicb_setup_host_only(C.byref(p), img_ptr, w, h, nch, C.byref(c), *ptrs))
+    return _constants_to_dict(c), (tuple(tabs) if image is not None else None)
+
+
+class ZoicCamera:
+    """One zoic camera node living on one CUDA device."""
+
+    def __init__(self, image=None, device=0, mode=None, **kw):
+        self.lib = capi.load()
+        self.params = make_params(**kw)
+        self.device = int(device)
+        img_ptr, w, h, nch = None, 0, 0, 0
+        if image is not None:
+            self._img = np.ascontiguousarray(image, np.float32)
+            h, w, nch = self._img.shape
+            img_ptr = self._img.ctypes.data
+        ctx = C.c_void_p()
+        capi.check(self.lib.zoicb_create(C.byref(self.params), img_ptr, w, h, nch, self.device, C.byref(ctx)))
+        self.ctx = ctx
+        if mode is not None:
+            self.set_mode(mode)
+
+    # -- configuration -------------------------------------------------------------------------
+    def set_mode(self, mode):
+        capi.check(self.lib.zoicb_set_mode(self.ctx, int(mode)))
+
+    @property
+    def mode(self):
+        return self.lib.zoicb_get_mode(self.ctx)
+
+    def constants(self):
+        c = capi.Constants()
+        capi.check(self.lib.zoicb_get_constants(self.ctx, C.byref(c)))
+        return _constants_to_dict(c)
+
+    def bokeh_tables(self):
+        h, w = self._img.shape[:2]
+        tabs = [np.zeros(h, np.float32), np.zeros(h, np.int32), np.zeros(h * w, np.float32), np.zeros(h * w, np.int32)]
+        capi.check(self.lib.zoicb_get_bokeh_tables(self.ctx, *[t.ctypes.data for t in tabs]))
+        return tuple(tabs)
+
+    # -- the hot path ---------------------------------------------------------------------------
+    def create_rays(self, samples, seed=0, first_index=0, out=None, stream=None):
+        """camera_create_ray for a CUDA tensor of samples [n, 4] -> (origin_w [n, 4], dir_tries [n, 4])."""
+        import torch
+        assert samples.is_cuda and samples.dtype == torch.float32 and samples.is_contiguous()
+        assert samples.device.index == self.device
+        n = samples.numel() // 4
+        if out is None:
+            o = torch.empty((n, 4), dtype=torch.float32, device=samples.device)
+            d = torch.empty((n, 4), dtype=torch.float32, device=samples.device)
+        else:
+            o, d = out
+        if stream is None:
+            stream = torch.cuda.current_stream(samples.device).cuda_stream
+        capi.check(self.lib.zoicb_generate(self.ctx, samples.data_ptr(), n, first_index, seed,
+                                           o.data_ptr(), d.data_ptr(), C.c_void_p(stream)))
+        return o, d
+
+    def create_rays_host(self, samples, seed=0, first_index=0, out=None):
+        """The same for HOST memory (numpy arrays or CPU tensors; pinned memory is copied directly)."""
+        def ptr(a):
+            return a.data_ptr() if hasattr(a, "data_ptr") else a.ctypes.data
+        n = (samples.numel() if hasattr(samples, "numel") else samples.size) // 4
+        if out is None:
+            o = np.empty((n, 4), np.float32)
+            d = np.empty((n, 4), np.float32)
+        else:
+            o, d = out
+        capi.check(self.lib.zoicb_generate_host(self.ctx, ptr(samples), n, first_index, seed, ptr(o), ptr(d)))
+        return o, d
+
+    def synth_samples(self, W, H, spp, seed, first_index, n, out=None, stream=None):
+        """Synthetic (sx, sy, lensx, lensy) samples generated on the device."""
+        import torch
+        dev = torch.device("cuda", self.device)
+        if out is None:
+            out = torch.empty((n, 4), dtype=torch.float32, device=dev)
+        if stream is None:
+            stream = torch.cuda.current_stream(dev).cuda_stream
+        capi.check(self.lib.zoicb_synth_samples(self.ctx, W, H, spp, seed, first_index, n, out.data_ptr(),
+                                                C.c_void_p(stream)))
+        return out
+
+    def stats(self):
+        s = capi.Stats()
+        capi.check(self.lib.zoicb_get_stats(self.ctx, C.byref(s)))
+        return {k: int(getattr(s, k)) for k, _ in capi.Stats._fields_}
+
+    def reset_stats(self):
+        capi.check(self.lib.zoicb_reset_stats(self.ctx))
+
+    def close(self):
+        if getattr(self, "ctx", None):
+            self.lib.zoicb_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def kernel_launches():
+    return int(capi.load().zoicb_kernel_launches())
+
+
+def measure_fp32_peak(device=0):
+    v = C.c_double(0.0)
+    capi.check(capi.load().zoicb_measure_fp32_peak(device, C.byref(v)))
+    return v.value

@@ -1,0 +1,84 @@
+// camera_state.h -- plain-old-data camera state shared by the host setup code and the CUDA kernels.
+//
+// The host (host_setup.cpp) derives these constants bit-exactly the way the reference's node_update does
+// (reference src/zoic.cpp:1575-1720) and the kernels receive the whole struct as a __grid_constant__
+// kernel parameter (constant bank, broadcast to all lanes).
+#pragma once
+#include <stdint.h>
+
+namespace zoicb {
+
+constexpr int kMaxElements = 24;
+constexpr int kLutSize = 32;
+constexpr int kMaxTries = 25;  // reference src/zoic.cpp:1767
+
+// One refracting surface, rear element (nearest the sensor) first.  Everything the march needs per
+// element visit is precomputed once on the host with the reference's own rounding.
+struct Element {
+    float center;     // z of the sphere centre (src/zoic.cpp:963-969)
+    float radius;     // signed radius of curvature R, cm (the stop is the R = 9999.9 "sphere")
+    float radius2;    // fl(R*R)
+    float sgn;        // R < 0 ? -1 : 1
+    float rim2;       // accept iff hx^2+hy^2 <= rim2: largest float <= (aperture/2)^2 evaluated in double
+                      // (src/zoic.cpp:1114), min'ed with fl(userApertureRadius^2) on the stop (:1115)
+    float eta;        // ior_i / ior_next, or ior_i when the next medium is 1.0 (src/zoic.cpp:1013)
+    float eta2;       // fl(eta*eta)
+    float inv_radius; // fl(1/R)       (fast path only)
+    int32_t tir_possible;  // ior_i > ior_next (src/zoic.cpp:1019)
+    float rim2_guard;      // fast path: |h2 - rim2| below this => undecided
+    float pad0, pad1;
+};
+
+struct LensState {
+    int32_t count;
+    int32_t aperture_element;
+    int32_t use_lut;
+    int32_t lut_size;
+    float origin_shift;       // film plane z (negative), src/zoic.cpp:1675
+    float half_sensor;        // fl(sensorWidth * 0.5)
+    float first_aperture;     // lenses[0].aperture (a diameter used as a half extent -- kept)
+    float neg_first_thickness;  // -lenses[0].thickness
+    float user_aperture_radius;
+    float lut_scale[kLutSize];  // boundingBox2d::getMaxScale() per LUT entry (src/zoic.cpp:503-517)
+    float lut_cx[kLutSize];     // boundingBox2d::getCentroid().x per LUT entry
+    Element e[kMaxElements];
+};
+
+struct ThinState {
+    float tan_fov;          // src/zoic.cpp:1607
+    float aperture_radius;  // src/zoic.cpp:1608
+    float focal_distance;
+    float ov_distance;      // opticalVignettingDistance
+    float ov_radius_true;   // fl(apertureRadius * opticalVignettingRadius), src/zoic.cpp:1302
+    int32_t use_dof;
+    int32_t use_ov;         // opticalVignettingDistance > 0
+    int32_t pad;
+};
+
+// Image-based aperture sampling tables (device pointers), src/zoic.cpp:117-122
+struct BokehTables {
+    const float* cdf_row;        // [h]
+    const int32_t* row_indices;  // [h]
+    const float* cdf_column;     // [h*w], rows in ORIGINAL row order (indexed by actual row * w)
+    const uint16_t* rel_column;  // [h*w], columnIndices[c] - row*w
+    int32_t w, h;
+    int32_t valid;
+    int32_t pad;
+};
+
+struct CameraState {
+    int32_t lens_model;  // 0 thin lens, 1 raytraced
+    int32_t use_image;
+    float weight_scale;  // exposure: 1+e^2 (e>0), 1/(1+e^2) (e<0), 1 (src/zoic.cpp:1981-1987)
+    int32_t pad;
+    ThinState thin;
+    BokehTables bokeh;
+    LensState lens;
+};
+
+// per-launch counters, accumulated with one atomicAdd per block per counter
+struct DeviceStats {
+    unsigned long long rays, success, vignetted, tir, attempts, element_visits, exact_reruns, pad;
+};
+
+}  // namespace zoicb

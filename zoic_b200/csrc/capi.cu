@@ -1,0 +1,347 @@
+// capi.cu -- the C ABI declared in include/zoicb.h.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/zoicb.h"
+#include "host_setup.h"
+#include "kernels.h"
+
+using namespace zoicb;
+
+namespace {
+
+thread_local std::string g_last_error;
+std::atomic<uint64_t> g_launches{0};
+
+zoicb_status fail(zoicb_status code, const std::string& msg) {
+    g_last_error = msg;
+    return code;
+}
+zoicb_status cuda_fail(cudaError_t e, const char* what) {
+    return fail(ZOICB_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define ZCUDA(call, what)                                         \
+    do {                                                          \
+        cudaError_t e__ = (call);                                 \
+        if (e__ != cudaSuccess) return cuda_fail(e__, what);      \
+    } while (0)
+
+void count_launches(int k) { if (k > 0) g_launches.fetch_add((uint64_t)k, std::memory_order_relaxed); }
+
+}  // namespace
+
+struct zoicb_ctx {
+    int device = 0;
+    int mode = ZOICB_MODE_EXACT;
+    HostCamera host;
+    // device tables (bokeh)
+    float* d_cdf_row = nullptr;
+    int32_t* d_row_idx = nullptr;
+    float* d_cdf_col = nullptr;
+    uint16_t* d_rel_col = nullptr;
+    DeviceStats* d_stats = nullptr;
+    // host-buffer pipeline (zoicb_generate_host)
+    static constexpr int kSlots = 3;
+    uint64_t chunk = 0;
+    cudaStream_t streams[kSlots] = {nullptr, nullptr, nullptr};
+    float4* d_in[kSlots] = {nullptr, nullptr, nullptr};
+    float4* d_o[kSlots] = {nullptr, nullptr, nullptr};
+    float4* d_d[kSlots] = {nullptr, nullptr, nullptr};
+    float4* h_in[kSlots] = {nullptr, nullptr, nullptr};   // pinned staging, only for pageable callers
+    float4* h_o[kSlots] = {nullptr, nullptr, nullptr};
+    float4* h_d[kSlots] = {nullptr, nullptr, nullptr};
+    std::mutex host_mu;
+};
+
+namespace {
+
+// exit-pupil LUT candidates classified on the GPU; host replays the bbox update
+bool lut_trace_gpu(void* user, const LensState& lens, const float* film_x, int n_film, const uint32_t* draws,
+                   int per_film, uint8_t* accept) {
+    (void)user;
+    const size_t total = (size_t)n_film * per_film;
+    float* d_film = nullptr;
+    uint32_t* d_draws = nullptr;
+    uint8_t* d_acc = nullptr;
+    bool ok = false;
+    int launches = 0;
+    do {
+        if (cudaMalloc(&d_film, n_film * sizeof(float)) != cudaSuccess) break;
+        if (cudaMalloc(&d_draws, total * 2 * sizeof(uint32_t)) != cudaSuccess) break;
+        if (cudaMalloc(&d_acc, total) != cudaSuccess) break;
+        if (cudaMemcpy(d_film, film_x, n_film * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) break;
+        if (cudaMemcpy(d_draws, draws, total * 2 * sizeof(uint32_t), cudaMemcpyHostToDevice) != cudaSuccess) break;
+        if (launch_lut_trace(lens, d_film, n_film, per_film, d_draws, d_acc, nullptr, &launches) != cudaSuccess) break;
+        if (cudaMemcpy(accept, d_acc, total, cudaMemcpyDeviceToHost) != cudaSuccess) break;
+        ok = true;
+    } while (0);
+    count_launches(launches);
+    cudaFree(d_film);
+    cudaFree(d_draws);
+    cudaFree(d_acc);
+    if (!ok) cudaGetLastError();
+    return ok;
+}
+
+void free_ctx(zoicb_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaFree(c->d_cdf_row); cudaFree(c->d_row_idx); cudaFree(c->d_cdf_col); cudaFree(c->d_rel_col);
+    cudaFree(c->d_stats);
+    for (int s = 0; s < zoicb_ctx::kSlots; ++s) {
+        if (c->streams[s]) cudaStreamDestroy(c->streams[s]);
+        cudaFree(c->d_in[s]); cudaFree(c->d_o[s]); cudaFree(c->d_d[s]);
+        if (c->h_in[s]) cudaFreeHost(c->h_in[s]);
+        if (c->h_o[s]) cudaFreeHost(c->h_o[s]);
+        if (c->h_d[s]) cudaFreeHost(c->h_d[s]);
+    }
+    delete c;
+}
+
+bool is_pinned_host(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+
+}  // namespace
+
+extern "C" {
+
+void zoicb_default_params(zoicb_params* p) {
+    if (!p) return;
+    p->sensorWidth = 3.6f; p->sensorHeight = 2.4f; p->focalLength = 2.0f; p->fStop = 4.0f;
+    p->focalDistance = 100.0f; p->useImage = 0; p->lensModel = ZOICB_RAYTRACED; p->kolbSamplingLUT = 1;
+    p->useDof = 1; p->opticalVignettingDistance = 0.0f; p->opticalVignettingRadius = 1.0f;
+    p->exposureControl = 0.0f; p->lensDataPath = ""; p->bokehPath = "";
+}
+
+zoicb_status zoicb_create(const zoicb_params* params, const float* rgb, int width, int height, int nch, int device,
+                          zoicb_ctx** out) {
+    if (!params || !out) return fail(ZOICB_ERR_INVALID_ARGUMENT, "zoicb_create: null argument");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(ZOICB_ERR_CUDA, "zoicb_create: no CUDA device (libzoicb has no CPU fallback)");
+    }
+    if (device < 0 || device >= ndev) return fail(ZOICB_ERR_INVALID_ARGUMENT, "zoicb_create: bad device index");
+    ZCUDA(cudaSetDevice(device), "cudaSetDevice");
+    cudaDeviceProp prop;
+    ZCUDA(cudaGetDeviceProperties(&prop, device), "cudaGetDeviceProperties");
+    if (prop.major != 10) return fail(ZOICB_ERR_CUDA, "zoicb_create: kernels are built for sm_100a only; device is " + std::string(prop.name));
+
+    zoicb_ctx* c = new zoicb_ctx();
+    c->device = device;
+    std::string err;
+    zoicb_status rc = build_camera(*params, rgb, width, height, nch, &c->host, &err, lut_trace_gpu, nullptr);
+    if (rc != ZOICB_OK) { free_ctx(c); return fail(rc, "zoicb_create: " + err); }
+
+    auto bail = [&](cudaError_t ce, const char* what) { free_ctx(c); return cuda_fail(ce, what); };
+    if ((e = cudaMalloc(&c->d_stats, sizeof(DeviceStats))) != cudaSuccess) return bail(e, "cudaMalloc(stats)");
+    if ((e = cudaMemset(c->d_stats, 0, sizeof(DeviceStats))) != cudaSuccess) return bail(e, "cudaMemset(stats)");
+    const HostBokeh& hb = c->host.bokeh;
+    if (hb.valid()) {
+        const size_t np = (size_t)hb.w * hb.h;
+        std::vector<uint16_t> rel(np);
+        for (int r = 0; r < hb.h; ++r)
+            for (int k = 0; k < hb.w; ++k) {
+                // entry k of ORIGINAL row r (the reference indexes cdfColumn by actual row * width)
+                size_t i = (size_t)r * hb.w + k;
+                rel[i] = (uint16_t)(hb.column_indices[i] - r * hb.w);
+            }
+        if ((e = cudaMalloc(&c->d_cdf_row, hb.h * sizeof(float))) != cudaSuccess) return bail(e, "cudaMalloc");
+        if ((e = cudaMalloc(&c->d_row_idx, hb.h * sizeof(int32_t))) != cudaSuccess) return bail(e, "cudaMalloc");
+        if ((e = cudaMalloc(&c->d_cdf_col, np * sizeof(float))) != cudaSuccess) return bail(e, "cudaMalloc");
+        if ((e = cudaMalloc(&c->d_rel_col, np * sizeof(uint16_t))) != cudaSuccess) return bail(e, "cudaMalloc");
+        cudaMemcpy(c->d_cdf_row, hb.cdf_row.data(), hb.h * sizeof(float), cudaMemcpyHostToDevice);
+        cudaMemcpy(c->d_row_idx, hb.row_indices.data(), hb.h * sizeof(int32_t), cudaMemcpyHostToDevice);
+        cudaMemcpy(c->d_cdf_col, hb.cdf_column.data(), np * sizeof(float), cudaMemcpyHostToDevice);
+        if ((e = cudaMemcpy(c->d_rel_col, rel.data(), np * sizeof(uint16_t), cudaMemcpyHostToDevice)) != cudaSuccess)
+            return bail(e, "cudaMemcpy(bokeh tables)");
+        BokehTables& bt = c->host.state.bokeh;
+        bt.cdf_row = c->d_cdf_row; bt.row_indices = c->d_row_idx; bt.cdf_column = c->d_cdf_col; bt.rel_column = c->d_rel_col;
+        bt.w = hb.w; bt.h = hb.h; bt.valid = 1;
+    }
+    *out = c;
+    return ZOICB_OK;
+}
+
+void zoicb_destroy(zoicb_ctx* ctx) { free_ctx(ctx); }
+
+zoicb_status zoicb_set_mode(zoicb_ctx* ctx, int mode) {
+    if (!ctx) return fail(ZOICB_ERR_INVALID_ARGUMENT, "zoicb_set_mode: null context");
+    if (mode != ZOICB_MODE_EXACT && mode != ZOICB_MODE_GUARDED) return fail(ZOICB_ERR_INVALID_ARGUMENT, "zoicb_set_mode: unknown mode");
+    ctx->mode = mode;
+    return ZOICB_OK;
+}
+int zoicb_get_mode(const zoicb_ctx* ctx) { return ctx ? ctx->mode : -1; }
+
+zoicb_status zoicb_generate(zoicb_ctx* ctx, const void* d_samples, uint64_t n, uint64_t first_index, uint64_t rng_seed,
+                            void* d_origin_w, void* d_dir_tries, void* stream) {
+    if (!ctx) return fail(ZOICB_ERR_INVALID_ARGUMENT, "zoicb_generate: null context");
+    if (n == 0) return ZOICB_OK;
+    if (!d_samples || !d_origin_w || !d_dir_tries) return fail(ZOICB_ERR_INVALID_ARGUMENT, "zoicb_generate: null buffer");
+    ZCUDA(cudaSetDevice(ctx->device), "cudaSetDevice");
+    int launches = 0;
+    cudaError_t e = launch_generate(ctx->host.state, ctx->mode, (const float4*)d_samples, n, first_index, rng_seed,
+                                    (float4*)d_origin_w, (float4*)d_dir_tries, ctx->d_stats, (cudaStream_t)stream, &launches);
+    count_launches(launches);
+    if (e != cudaSuccess) return cuda_fail(e, "zoicb_generate launch");
+    return ZOICB_OK;
+}
+
+zoicb_status zoicb_generate_host(zoicb_ctx* ctx, const float* h_samples, uint64_t n, uint64_t first_index,
+                                 uint64_t rng_seed, float* h_origin_w, float* h_dir_tries) {
+    if (!ctx) return fail(ZOICB_ERR_INVALID_ARGUMENT, "zoicb_generate_host: null context");
+    if (n == 0) return ZOICB_OK;
+    if (!h_samples || !h_origin_w || !h_dir_tries) return fail(ZOICB_ERR_INVALID_ARGUMENT, "zoicb_generate_host: null buffer");
+    std::lock_guard<std::mutex> lock(ctx->host_mu);
+    ZCUDA(cudaSetDevice(ctx->device), "cudaSetDevice");
+    constexpr int K = zoicb_ctx::kSlots;
+    if (!ctx->chunk) {
+        ctx->chunk = 1ull << 22;  // 4 Mi samples: 64 MiB up, 128 MiB down per slot
+        for (int s = 0; s < K; ++s) {
+            ZCUDA(cudaStreamCreateWithFlags(&ctx->streams[s], cudaStreamNonBlocking), "cudaStreamCreate");
+            ZCUDA(cudaMalloc(&ctx->d_in[s], ctx->chunk * sizeof(float4)), "cudaMalloc(staging)");
+            ZCUDA(cudaMalloc(&ctx->d_o[s], ctx->chunk * sizeof(float4)), "cudaMalloc(staging)");
+            ZCUDA(cudaMalloc(&ctx->d_d[s], ctx->chunk * sizeof(float4)), "cudaMalloc(staging)");
+        }
+    }
+    const bool direct = is_pinned_host(h_samples) && is_pinned_host(h_origin_w) && is_pinned_host(h_dir_tries);
+    if (!direct && !ctx->h_in[0]) {
+        for (int s = 0; s < K; ++s) {
+            ZCUDA(cudaMallocHost(&ctx->h_in[s], ctx->chunk * sizeof(float4)), "cudaMallocHost");
+            ZCUDA(cudaMallocHost(&ctx->h_o[s], ctx->chunk * sizeof(float4)), "cudaMallocHost");
+            ZCUDA(cudaMallocHost(&ctx->h_d[s], ctx->chunk * sizeof(float4)), "cudaMallocHost");
+        }
+    }
+    const uint64_t nchunks = (n + ctx->chunk - 1) / ctx->chunk;
+    int launches = 0;
+    // pageable callers: the copy-out of chunk k-K is drained just before slot reuse
+    auto drain = [&](uint64_t k) -> cudaError_t {
+        const int s = (int)(k % K);
+        cudaError_t e = cudaStreamSynchronize(ctx->streams[s]);
+        if (e != cudaSuccess) return e;
+        if (!direct) {
+            const uint64_t b = k * ctx->chunk, m = (n - b < ctx->chunk) ? n - b : ctx->chunk;
+            std::memcpy(h_origin_w + 4 * b, ctx->h_o[s], m * sizeof(float4));
+            std::memcpy(h_dir_tries + 4 * b, ctx->h_d[s], m * sizeof(float4));
+        }
+        return cudaSuccess;
+    };
+    for (uint64_t k = 0; k < nchunks; ++k) {
+        const int s = (int)(k % K);
+        if (k >= (uint64_t)K) ZCUDA(drain(k - K), "pipeline drain");
+        const uint64_t b = k * ctx->chunk, m = (n - b < ctx->chunk) ? n - b : ctx->chunk;
+        const float* src = h_samples + 4 * b;
+        if (!direct) { std::memcpy(ctx->h_in[s], src, m * sizeof(float4)); src = (const float*)ctx->h_in[s]; }
+        ZCUDA(cudaMemcpyAsync(ctx->d_in[s], src, m * sizeof(float4), cudaMemcpyHostToDevice, ctx->streams[s]), "H2D");
+        cudaError_t e = launch_generate(ctx->host.state, ctx->mode, ctx->d_in[s], m, first_index + b, rng_seed, ctx->d_o[s],
+                                        ctx->d_d[s], ctx->d_stats, ctx->streams[s], &launches);
+        if (e != cudaSuccess) { count_launches(launches); return cuda_fail(e, "zoicb_generate_host launch"); }
+        float* dst_o = direct ? h_origin_w + 4 * b : (float*)ctx->h_o[s];
+        float* dst_d = direct ? h_dir_tries + 4 * b : (float*)ctx->h_d[s];
+        ZCUDA(cudaMemcpyAsync(dst_o, ctx->d_o[s], m * sizeof(float4), cudaMemcpyDeviceToHost, ctx->streams[s]), "D2H");
+        ZCUDA(cudaMemcpyAsync(dst_d, ctx->d_d[s], m * sizeof(float4), cudaMemcpyDeviceToHost, ctx->streams[s]), "D2H");
+    }
+    count_launches(launches);
+    for (uint64_t k = (nchunks > (uint64_t)K ? nchunks - K : 0); k < nchunks; ++k) ZCUDA(drain(k), "pipeline drain");
+    return ZOICB_OK;
+}
+
+zoicb_status zoicb_synth_samples(zoicb_ctx* ctx, uint32_t W, uint32_t H, uint32_t spp, uint64_t seed, uint64_t first_index,
+                                 uint64_t n, void* d_samples, void* stream) {
+    if (!ctx) return fail(ZOICB_ERR_INVALID_ARGUMENT, "zoicb_synth_samples: null context");
+    if (!W || !H || !spp) return fail(ZOICB_ERR_INVALID_ARGUMENT, "zoicb_synth_samples: zero dimension");
+    if (n == 0) return ZOICB_OK;
+    if (!d_samples) return fail(ZOICB_ERR_INVALID_ARGUMENT, "zoicb_synth_samples: null buffer");
+    ZCUDA(cudaSetDevice(ctx->device), "cudaSetDevice");
+    int launches = 0;
+    cudaError_t e = launch_synth(W, H, spp, seed, first_index, n, (float4*)d_samples, (cudaStream_t)stream, &launches);
+    count_launches(launches);
+    if (e != cudaSuccess) return cuda_fail(e, "zoicb_synth_samples launch");
+    return ZOICB_OK;
+}
+
+zoicb_status zoicb_get_stats(zoicb_ctx* ctx, zoicb_stats* out) {
+    if (!ctx || !out) return fail(ZOICB_ERR_INVALID_ARGUMENT, "zoicb_get_stats: null argument");
+    ZCUDA(cudaSetDevice(ctx->device), "cudaSetDevice");
+    ZCUDA(cudaDeviceSynchronize(), "cudaDeviceSynchronize");
+    DeviceStats h;
+    ZCUDA(cudaMemcpy(&h, ctx->d_stats, sizeof h, cudaMemcpyDeviceToHost), "cudaMemcpy(stats)");
+    out->rays = h.rays; out->success = h.success; out->vignetted = h.vignetted;
+    out->total_internal_reflection = h.tir; out->attempts = h.attempts; out->element_visits = h.element_visits;
+    out->exact_reruns = h.exact_reruns;
+    return ZOICB_OK;
+}
+
+zoicb_status zoicb_reset_stats(zoicb_ctx* ctx) {
+    if (!ctx) return fail(ZOICB_ERR_INVALID_ARGUMENT, "zoicb_reset_stats: null context");
+    ZCUDA(cudaSetDevice(ctx->device), "cudaSetDevice");
+    ZCUDA(cudaDeviceSynchronize(), "cudaDeviceSynchronize");
+    ZCUDA(cudaMemset(ctx->d_stats, 0, sizeof(DeviceStats)), "cudaMemset(stats)");
+    return ZOICB_OK;
+}
+
+zoicb_status zoicb_get_constants(const zoicb_ctx* ctx, zoicb_constants* out) {
+    if (!ctx || !out) return fail(ZOICB_ERR_INVALID_ARGUMENT, "zoicb_get_constants: null argument");
+    *out = ctx->host.constants;
+    return ZOICB_OK;
+}
+
+zoicb_status zoicb_get_bokeh_tables(const zoicb_ctx* ctx, float* cdfRow, int32_t* rowIndices, float* cdfColumn,
+                                    int32_t* columnIndices) {
+    if (!ctx) return fail(ZOICB_ERR_INVALID_ARGUMENT, "zoicb_get_bokeh_tables: null context");
+    const HostBokeh& hb = ctx->host.bokeh;
+    if (!hb.valid()) return fail(ZOICB_ERR_BOKEH_IMAGE, "zoicb_get_bokeh_tables: camera has no bokeh image");
+    const size_t np = (size_t)hb.w * hb.h;
+    if (cdfRow) std::memcpy(cdfRow, hb.cdf_row.data(), hb.h * sizeof(float));
+    if (rowIndices) std::memcpy(rowIndices, hb.row_indices.data(), hb.h * sizeof(int32_t));
+    if (cdfColumn) std::memcpy(cdfColumn, hb.cdf_column.data(), np * sizeof(float));
+    if (columnIndices) std::memcpy(columnIndices, hb.column_indices.data(), np * sizeof(int32_t));
+    return ZOICB_OK;
+}
+
+zoicb_status zoicb_setup_host_only(const zoicb_params* params, const float* rgb, int width, int height, int nch,
+                                   zoicb_constants* out, float* cdfRow, int32_t* rowIndices, float* cdfColumn,
+                                   int32_t* columnIndices) {
+    if (!params || !out) return fail(ZOICB_ERR_INVALID_ARGUMENT, "zoicb_setup_host_only: null argument");
+    HostCamera hc;
+    std::string err;
+    zoicb_status rc = build_camera(*params, rgb, width, height, nch, &hc, &err, nullptr, nullptr);
+    if (rc != ZOICB_OK) return fail(rc, "zoicb_setup_host_only: " + err);
+    *out = hc.constants;
+    const HostBokeh& hb = hc.bokeh;
+    if (hb.valid()) {
+        const size_t np = (size_t)hb.w * hb.h;
+        if (cdfRow) std::memcpy(cdfRow, hb.cdf_row.data(), hb.h * sizeof(float));
+        if (rowIndices) std::memcpy(rowIndices, hb.row_indices.data(), hb.h * sizeof(int32_t));
+        if (cdfColumn) std::memcpy(cdfColumn, hb.cdf_column.data(), np * sizeof(float));
+        if (columnIndices) std::memcpy(columnIndices, hb.column_indices.data(), np * sizeof(int32_t));
+    }
+    return ZOICB_OK;
+}
+
+zoicb_status zoicb_measure_fp32_peak(int device, double* tflops) {
+    if (!tflops) return fail(ZOICB_ERR_INVALID_ARGUMENT, "zoicb_measure_fp32_peak: null argument");
+    ZCUDA(cudaSetDevice(device), "cudaSetDevice");
+    int launches = 0;
+    cudaError_t e = measure_fp32_peak(tflops, &launches);
+    count_launches(launches);
+    if (e != cudaSuccess) return cuda_fail(e, "zoicb_measure_fp32_peak");
+    return ZOICB_OK;
+}
+
+uint64_t zoicb_kernel_launches(void) { return g_launches.load(std::memory_order_relaxed); }
+const char* zoicb_last_error(void) { return g_last_error.c_str(); }
+const char* zoicb_version(void) { return "zoicb 0.1 (sm_100a)"; }
+
+}  // extern "C"

@@ -1,0 +1,408 @@
+// kernels.cu -- sm_100a kernels for batched camera_create_ray.
+//
+// Behavioural reference: camera_create_ray, reference src/zoic.cpp:1752-1990 (thin-lens branch
+// :1771-1848, raytraced branch :1850-1964, tail :1974-1987) and its callees.
+//
+// Data layout in HBM: samples float4 (sx, sy, lensx, lensy); outputs two float4
+// arrays (origin.xyz, weight) and (dir.xyz, tries), index = sample index, so a warp reads 512 B and
+// writes 2 x 512 B contiguous.  Camera constants travel as a __grid_constant__ kernel parameter.
+#include <cuda_runtime.h>
+#include <math_constants.h>
+
+#include "kernels.h"
+#include "lens_math.cuh"
+
+namespace zoicb {
+
+// ------------------------------------------------------------------------------------------------
+// image-based aperture sampling (reference imageData::bokehSample, src/zoic.cpp:420-485)
+// ------------------------------------------------------------------------------------------------
+// std::upper_bound's probe sequence: first index whose value is greater than u
+__device__ __forceinline__ int upper_bound_idx(const float* __restrict__ a, int len, float u) {
+    int first = 0;
+    while (len > 0) {
+        int half = len >> 1;
+        int mid = first + half;
+        if (u < a[mid]) {
+            len = half;
+        } else {
+            first = mid + 1;
+            len = len - half - 1;
+        }
+    }
+    return first;
+}
+
+struct BokehView {
+    const float* cdf_row;     // shared memory when staged, else global
+    const int32_t* row_idx;
+    const float* cdf_col;     // global (L1/L2 resident)
+    const uint16_t* rel_col;
+    int w, h;
+};
+
+__device__ __forceinline__ void bokeh_sample(const BokehView& b, float u_row, float u_col, float* dx, float* dy) {
+    int r = upper_bound_idx(b.cdf_row, b.h, u_row);
+    if (r >= b.h) r = b.h - 1;
+    const int row = b.row_idx[r];
+    const int rrow = row - ((b.w - 1) / 2);  // centred with the WIDTH (:441)
+    const int start = row * b.w;
+    int c = upper_bound_idx(b.cdf_col + start, b.w, u_col);
+    if (c >= b.w) c = b.w - 1;
+    const int rel = (int)__ldg(b.rel_col + start + c);
+    const int rcol = rel - ((b.h - 1) / 2);  // centred with the HEIGHT (:466)
+    const float fr = (float)rcol;
+    const float fc = xmul((float)rrow, -1.0f);
+    *dx = xmul(xdiv(fr, (float)b.w), 2.0f);
+    *dy = xmul(xdiv(fc, (float)b.h), 2.0f);
+}
+
+template <bool kImage>
+__device__ __forceinline__ void lens_sample(const BokehView& b, float u, float v, float* lx, float* ly) {
+    if (kImage) bokeh_sample(b, u, v, lx, ly);
+    else concentric_disk(u, v, lx, ly);
+}
+
+// two draws of the per-sample stream; the FIRST draw feeds the SECOND parameter (g++ evaluates the
+// reference's argument lists right to left; pinned in tests/test_oracle_port_vs_ref.py)
+__device__ __forceinline__ void draw_pair(Xor128& rng, float* first_param, float* second_param) {
+    uint32_t k1 = xor128_next(rng);
+    uint32_t k2 = xor128_next(rng);
+    *second_param = u32_to_unit(k1);
+    *first_param = u32_to_unit(k2);
+}
+
+__device__ __forceinline__ BokehView stage_bokeh(const CameraState& cam, float* smem, bool staged) {
+    BokehView b;
+    b.w = cam.bokeh.w; b.h = cam.bokeh.h;
+    b.cdf_col = cam.bokeh.cdf_column;
+    b.rel_col = cam.bokeh.rel_column;
+    if (staged) {
+        float* s_cdf = smem;
+        int32_t* s_idx = reinterpret_cast<int32_t*>(smem + b.h);
+        for (int i = threadIdx.x; i < b.h; i += blockDim.x) {
+            s_cdf[i] = cam.bokeh.cdf_row[i];
+            s_idx[i] = cam.bokeh.row_indices[i];
+        }
+        __syncthreads();
+        b.cdf_row = s_cdf;
+        b.row_idx = s_idx;
+    } else {
+        b.cdf_row = cam.bokeh.cdf_row;
+        b.row_idx = cam.bokeh.row_indices;
+    }
+    return b;
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-block counter reduction: warp shuffle -> shared -> one atomicAdd per counter per block
+// ------------------------------------------------------------------------------------------------
+struct LocalStats { unsigned rays, success, vignetted, tir, attempts, visits, reruns; };
+
+__device__ __forceinline__ void flush_stats(const LocalStats& ls, DeviceStats* g) {
+    __shared__ unsigned long long s_acc[7];
+    if (threadIdx.x < 7) s_acc[threadIdx.x] = 0ull;
+    __syncthreads();
+    unsigned v[7] = {ls.rays, ls.success, ls.vignetted, ls.tir, ls.attempts, ls.visits, ls.reruns};
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
+        unsigned s = __reduce_add_sync(0xffffffffu, v[k]);
+        if ((threadIdx.x & 31) == 0 && s) atomicAdd(&s_acc[k], (unsigned long long)s);
+    }
+    __syncthreads();
+    if (threadIdx.x < 7 && s_acc[threadIdx.x]) {
+        unsigned long long* dst = &g->rays + threadIdx.x;
+        atomicAdd(dst, s_acc[threadIdx.x]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// EXACT thin lens (src/zoic.cpp:1771-1848, :1297-1305)
+// ------------------------------------------------------------------------------------------------
+template <bool kImage>
+__global__ void __launch_bounds__(256)
+thin_exact_kernel(const __grid_constant__ CameraState cam, const float4* __restrict__ samples, uint64_t n,
+                  uint64_t first_index, uint64_t seed, float4* __restrict__ origin_w, float4* __restrict__ dir_tries,
+                  DeviceStats* stats, int stage_rows) {
+    extern __shared__ float smem[];
+    BokehView bk;
+    if (kImage) bk = stage_bokeh(cam, smem, stage_rows != 0);
+    const ThinState& T = cam.thin;
+    LocalStats ls = {0, 0, 0, 0, 0, 0, 0};
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const float4 s = __ldcs(samples + i);
+        Vec3 p = vmake(xmul(s.x, T.tan_fov), xmul(s.y, T.tan_fov), 1.0f);
+        const Vec3 dir0 = vnormalize(p);  // p - origin0 with origin0 = 0
+        Vec3 origin = vmake(0.0f, 0.0f, 0.0f);
+        Vec3 dir = dir0;
+        int tries = 0;
+        float weight = 1.0f;
+        ls.rays++;
+        ls.attempts++;
+        if (T.use_dof) {
+            float lx, ly;
+            lens_sample<kImage>(bk, s.z, s.w, &lx, &ly);
+            const float inter = fabsf(xdiv(T.focal_distance, dir0.z));
+            const Vec3 focus = vscale(dir0, inter);
+            origin = vmake(xmul(lx, T.aperture_radius), xmul(ly, T.aperture_radius), 0.0f);
+            dir = vnormalize(vsub(focus, origin));
+            if (T.use_ov) {
+                Xor128 rng = sample_stream(seed, first_index + i);
+                while (tries <= kMaxTries) {
+                    // empericalOpticalVignetting
+                    float qx = xsub(xmul(dir.x, T.ov_distance), origin.x);
+                    float qy = xsub(xmul(dir.y, T.ov_distance), origin.y);
+                    float hyp = xsqrt(xadd(xmul(qx, qx), xmul(qy, qy)));
+                    if (fabsf(hyp) < T.ov_radius_true) break;
+                    float u, v;
+                    draw_pair(rng, &u, &v);
+                    lens_sample<kImage>(bk, u, v, &lx, &ly);
+                    origin = vmake(xmul(lx, T.aperture_radius), xmul(ly, T.aperture_radius), 0.0f);
+                    dir = vnormalize(vsub(focus, origin));
+                    ++tries;
+                    ls.attempts++;
+                }
+            }
+            if (tries > kMaxTries) { weight = 0.0f; ls.vignetted++; }
+            else ls.success++;
+        }
+        dir.z = -dir.z;
+        weight = xmul(weight, cam.weight_scale);
+        __stcs(origin_w + i, make_float4(origin.x, origin.y, origin.z, weight));
+        __stcs(dir_tries + i, make_float4(dir.x, dir.y, dir.z, (float)tries));
+    }
+    flush_stats(ls, stats);
+}
+
+// ------------------------------------------------------------------------------------------------
+// EXACT raytraced lens (src/zoic.cpp:1850-1964, :1099-1158)
+// ------------------------------------------------------------------------------------------------
+template <bool kImage, bool kLut>
+__global__ void __launch_bounds__(256)
+kolb_exact_kernel(const __grid_constant__ CameraState cam, const float4* __restrict__ samples, uint64_t n,
+                  uint64_t first_index, uint64_t seed, float4* __restrict__ origin_w, float4* __restrict__ dir_tries,
+                  DeviceStats* stats, int stage_rows) {
+    extern __shared__ float smem[];
+    BokehView bk;
+    if (kImage) bk = stage_bokeh(cam, smem, stage_rows != 0);
+    const LensState& L = cam.lens;
+    LocalStats ls = {0, 0, 0, 0, 0, 0, 0};
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const float4 s = __ldcs(samples + i);
+        const Vec3 film = vmake(xmul(s.x, L.half_sensor), xmul(s.y, L.half_sensor), L.origin_shift);  // :1853-1855
+        float lx, ly;
+        lens_sample<kImage>(bk, s.z, s.w, &lx, &ly);
+        float max_scale = L.first_aperture, translation = 0.0f, sn = 0.0f, cs = 1.0f;
+        Ray r;
+        r.o = film;
+        if (kLut) {
+            const float dist = fabsf(xsqrt(xadd(xmul(film.x, film.x), xmul(film.y, film.y))));
+            lut_lookup(L, dist, &max_scale, &translation);
+            const float theta = __double2float_rn(atan2((double)film.y, (double)film.x));  // :1899
+            sn = fast_sin(theta);
+            cs = fast_cos(theta);
+            float px = xadd(xmul(lx, max_scale), translation);  // :1913-1914 (translation on x only)
+            float py = xmul(ly, max_scale);
+            float rx = xsub(xmul(px, cs), xmul(py, sn));
+            float ry = xadd(xmul(px, sn), xmul(py, cs));
+            r.d = vmake(xsub(rx, film.x), xsub(ry, film.y), L.neg_first_thickness);
+        } else {
+            r.d = vmake(xsub(xmul(lx, max_scale), film.x), xsub(xmul(ly, max_scale), film.y), L.neg_first_thickness);
+        }
+        int tries = 0;
+        Xor128 rng = sample_stream(seed, first_index + i);
+        ls.rays++;
+        for (;;) {
+            int visited;
+            const int rc = exact_march(L, r, &visited);
+            ls.attempts++;
+            ls.visits += visited;
+            if (rc == kTir) ls.tir++;
+            if (rc == kPass || tries > kMaxTries) break;
+            float u, v;
+            draw_pair(rng, &u, &v);
+            lens_sample<kImage>(bk, u, v, &lx, &ly);
+            r.o = film;
+            if (kLut) {
+                float px = xadd(xmul(lx, max_scale), translation);  // :1932-1933 (scalar += on BOTH components)
+                float py = xadd(xmul(ly, max_scale), translation);
+                float rx = xsub(xmul(px, cs), xmul(py, sn));
+                float ry = xadd(xmul(px, sn), xmul(py, cs));
+                r.d = vmake(xsub(rx, film.x), xsub(ry, film.y), L.neg_first_thickness);
+            } else {
+                r.d = vmake(xsub(xmul(lx, max_scale), film.x), xsub(xmul(ly, max_scale), film.y), L.neg_first_thickness);
+            }
+            ++tries;
+        }
+        float weight = 1.0f;
+        if (tries > kMaxTries) { weight = 0.0f; ls.vignetted++; }
+        else ls.success++;
+        weight = xmul(weight, cam.weight_scale);
+        // flip to look down -Z (:1960-1961)
+        __stcs(origin_w + i, make_float4(-r.o.x, -r.o.y, -r.o.z, weight));
+        __stcs(dir_tries + i, make_float4(-r.d.x, -r.d.y, -r.d.z, (float)tries));
+    }
+    flush_stats(ls, stats);
+}
+
+// ------------------------------------------------------------------------------------------------
+// synthetic samples
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+synth_samples_kernel(uint32_t W, uint32_t H, uint32_t spp, uint64_t seed, uint64_t first_index, uint64_t n,
+                     float4* __restrict__ out) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
+        const uint64_t i = first_index + j;
+        const uint64_t pix = i / spp;
+        const uint32_t px = (uint32_t)(pix % W), py = (uint32_t)((pix / W) % H);
+        const uint64_t g0 = mix64((seed ^ 0xA5A5A5A55A5A5A5Aull) + ZOICB_GOLDEN * (i + 1));
+        const uint64_t g1 = mix64(g0 + ZOICB_GOLDEN);
+        const float inv24 = 1.0f / 16777216.0f;
+        const float u0 = xmul((float)(uint32_t)(g0 & 0xFFFFFF), inv24);
+        const float u1 = xmul((float)(uint32_t)((g0 >> 32) & 0xFFFFFF), inv24);
+        const float u2 = xmul((float)(uint32_t)(g1 & 0xFFFFFF), inv24);
+        const float u3 = xmul((float)(uint32_t)((g1 >> 32) & 0xFFFFFF), inv24);
+        const float fx = xadd((float)px, u0);
+        const float fy = xadd((float)py, u1);
+        float4 o;
+        o.x = xsub(xdiv(xmul(2.0f, fx), (float)W), 1.0f);
+        o.y = xmul(xsub(1.0f, xdiv(xmul(2.0f, fy), (float)H)), xdiv((float)H, (float)W));
+        o.z = u2;
+        o.w = u3;
+        out[j] = o;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// exit-pupil LUT candidates (src/zoic.cpp:1409-1421): classify n_film x per_film rays
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+lut_trace_kernel(const __grid_constant__ LensState L, const float* __restrict__ film_x, int n_film, int per_film,
+                 const uint32_t* __restrict__ draws, uint8_t* __restrict__ accept) {
+    const size_t total = (size_t)n_film * per_film;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += stride) {
+        const int f = (int)(idx / per_film);
+        const uint2 k = reinterpret_cast<const uint2*>(draws)[idx];
+        const float U = xsub(xmul(u32_to_unit(k.x), 2.0f), 1.0f);
+        const float V = xsub(xmul(u32_to_unit(k.y), 2.0f), 1.0f);
+        Ray r;
+        r.o = vmake(film_x[f], 0.0f, L.origin_shift);
+        r.d = vmake(xsub(xmul(U, L.first_aperture), r.o.x), xsub(xmul(V, L.first_aperture), r.o.y), L.neg_first_thickness);
+        int visited;
+        accept[idx] = exact_march(L, r, &visited) == kPass ? 1 : 0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// fp32 peak probe: 8 independent FFMA chains per thread
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) ffma_peak_kernel(float* out, int iters, float a, float b) {
+    float x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            x0 = fmaf(x0, a, b); x1 = fmaf(x1, a, b); x2 = fmaf(x2, a, b); x3 = fmaf(x3, a, b);
+            x4 = fmaf(x4, a, b); x5 = fmaf(x5, a, b); x6 = fmaf(x6, a, b); x7 = fmaf(x7, a, b);
+        }
+    }
+    float s = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+    if (s == 123.456f) out[0] = s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// launchers
+// ------------------------------------------------------------------------------------------------
+static int g_sm_count = 0;
+static int sm_count() {
+    if (!g_sm_count) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
+        if (g_sm_count <= 0) g_sm_count = 148;
+    }
+    return g_sm_count;
+}
+
+static unsigned grid_for(uint64_t n, int threads, int ctas_per_sm) {
+    uint64_t want = (n + threads - 1) / threads;
+    uint64_t cap = (uint64_t)sm_count() * ctas_per_sm;  // whole waves of resident CTAs, grid-stride beyond
+    return (unsigned)(want < cap ? (want ? want : 1) : cap);
+}
+
+cudaError_t launch_generate(const CameraState& cam, int mode, const float4* samples, uint64_t n, uint64_t first_index,
+                            uint64_t seed, float4* origin_w, float4* dir_tries, DeviceStats* stats, cudaStream_t st,
+                            int* launches) {
+    if (n == 0) return cudaSuccess;
+    (void)mode;
+    const int threads = 256;
+    const bool image = cam.use_image != 0;
+    size_t smem = 0;
+    int stage = 0;
+    if (image) {
+        size_t need = (size_t)cam.bokeh.h * 8;
+        if (need <= 40 * 1024) { smem = need; stage = 1; }
+    }
+    const unsigned grid = grid_for(n, threads, 8);
+    if (cam.lens_model == 0) {
+        if (image) thin_exact_kernel<true><<<grid, threads, smem, st>>>(cam, samples, n, first_index, seed, origin_w, dir_tries, stats, stage);
+        else thin_exact_kernel<false><<<grid, threads, 0, st>>>(cam, samples, n, first_index, seed, origin_w, dir_tries, stats, 0);
+    } else {
+        const bool lut = cam.lens.use_lut != 0;
+        if (image && lut) kolb_exact_kernel<true, true><<<grid, threads, smem, st>>>(cam, samples, n, first_index, seed, origin_w, dir_tries, stats, stage);
+        else if (image) kolb_exact_kernel<true, false><<<grid, threads, smem, st>>>(cam, samples, n, first_index, seed, origin_w, dir_tries, stats, stage);
+        else if (lut) kolb_exact_kernel<false, true><<<grid, threads, 0, st>>>(cam, samples, n, first_index, seed, origin_w, dir_tries, stats, 0);
+        else kolb_exact_kernel<false, false><<<grid, threads, 0, st>>>(cam, samples, n, first_index, seed, origin_w, dir_tries, stats, 0);
+    }
+    if (launches) *launches += 1;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_synth(uint32_t W, uint32_t H, uint32_t spp, uint64_t seed, uint64_t first_index, uint64_t n,
+                         float4* out, cudaStream_t st, int* launches) {
+    if (n == 0) return cudaSuccess;
+    synth_samples_kernel<<<grid_for(n, 256, 8), 256, 0, st>>>(W, H, spp, seed, first_index, n, out);
+    if (launches) *launches += 1;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_lut_trace(const LensState& L, const float* d_film_x, int n_film, int per_film, const uint32_t* d_draws,
+                             uint8_t* d_accept, cudaStream_t st, int* launches) {
+    lut_trace_kernel<<<grid_for((uint64_t)n_film * per_film, 256, 8), 256, 0, st>>>(L, d_film_x, n_film, per_film, d_draws, d_accept);
+    if (launches) *launches += 1;
+    return cudaGetLastError();
+}
+
+cudaError_t measure_fp32_peak(double* tflops, int* launches) {
+    float* d = nullptr;
+    cudaError_t e = cudaMalloc(&d, 4);
+    if (e != cudaSuccess) return e;
+    const int iters = 4096, blocks = sm_count() * 8, threads = 256;
+    cudaEvent_t a, b;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    double best = 0.0;
+    for (int rep = 0; rep < 5; ++rep) {
+        cudaEventRecord(a);
+        ffma_peak_kernel<<<blocks, threads>>>(d, iters, 1.0000001f, 1e-7f);
+        cudaEventRecord(b);
+        e = cudaEventSynchronize(b);
+        if (e != cudaSuccess) break;
+        float ms = 0;
+        cudaEventElapsedTime(&ms, a, b);
+        double flops = 2.0 * 8 * 16 * (double)iters * blocks * threads;
+        double tf = flops / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;
+        if (launches) *launches += 1;
+    }
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    cudaFree(d);
+    *tflops = best;
+    return e;
+}
+
+}  // namespace zoicb

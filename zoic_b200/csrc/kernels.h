@@ -1,0 +1,19 @@
+// kernels.h -- launchers for the sm_100a kernels (kernels.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "camera_state.h"
+
+namespace zoicb {
+
+cudaError_t launch_generate(const CameraState& cam, int mode, const float4* samples, uint64_t n, uint64_t first_index,
+                            uint64_t seed, float4* origin_w, float4* dir_tries, DeviceStats* stats, cudaStream_t st,
+                            int* launches);
+cudaError_t launch_synth(uint32_t W, uint32_t H, uint32_t spp, uint64_t seed, uint64_t first_index, uint64_t n,
+                         float4* out, cudaStream_t st, int* launches);
+cudaError_t launch_lut_trace(const LensState& L, const float* d_film_x, int n_film, int per_film, const uint32_t* d_draws,
+                             uint8_t* d_accept, cudaStream_t st, int* launches);
+cudaError_t measure_fp32_peak(double* tflops, int* launches);
+
+}  // namespace zoicb
