@@ -118,6 +118,10 @@ ZOICB_API void zoicb_destroy(zoicb_ctx* ctx);
 
 ZOICB_API zoicb_status zoicb_set_mode(zoicb_ctx* ctx, int mode);
 ZOICB_API int zoicb_get_mode(const zoicb_ctx* ctx);
+/* Validation hook: multiply every decision margin of the GUARDED mode by `scale` (1 = shipped margins,
+ * 0 = no margins: plain fast arithmetic whose path flips tests/ and tools/validate_guarded.py count to show
+ * how much head-room the shipped margins have).  Not meant to be called while generate calls are in flight. */
+ZOICB_API zoicb_status zoicb_set_guard_scale(zoicb_ctx* ctx, float scale);
 
 /* camera_create_ray for a flat batch.  All pointers are DEVICE pointers owned by the caller:
  *   d_samples    n x float4 (sx, sy, lensx, lensy)          -- AtCameraInput fields zoic reads

@@ -147,3 +147,52 @@ def test_empty_batch_and_errors():
     with pytest.raises(capi.ZoicError) as e:
         ZoicCamera(lensModel=0, useImage=1)
     assert e.value.code == capi.ERR_BOKEH_IMAGE
+
+
+# ---------------------------------------------------------------------------------------------------
+# GUARDED mode (the default): fused fast path + exact re-run of undecided samples.  Same decision sequence
+# as the oracle (zero path flips: weight and tries identical everywhere, counters identical), values within
+# the north-star tolerance: |d_origin| <= 1e-5 * max(|origin|, 1 cm), |d_dir| <= 1e-5 per ray.
+# ---------------------------------------------------------------------------------------------------
+def _check_guarded(kw, port, n=400_000, seed=21, image=None):
+    from zoic_b200 import ZoicCamera, MODE_GUARDED
+    cam = ZoicCamera(image=image, **kw)
+    assert cam.mode == MODE_GUARDED  # the default
+    ref = port.PortCamera(image=image, **kw)
+    s = random_samples(n, seed=seed)
+    o, d, st = _run_gpu(cam, s, seed=seed, first_index=999)
+    o2, d2, st2 = ref.generate(s, seed=seed, first_index=999, nthreads=8)
+    res = compare_rays(o, d, o2, d2, tol=1e-5)
+    assert res["path_flips"] == 0 and res["out_of_tol"] == 0, res
+    assert st["rays"] == n and st["attempts"] == st2["attempts"] and st["element_visits"] == st2["element_visits"]
+    assert st["success"] == st2["success"] and st["vignetted"] == st2["vignetted"]
+    assert st["total_internal_reflection"] == st2["tir"]
+    cam.close()
+    ref.close()
+    return res, st
+
+
+@pytest.mark.parametrize("lens", ["double_gauss_f2.0.dat", "fisheye_muller_f4.0.dat", "petzval_f1.6.dat",
+                                  "telephoto_f5.0.dat", "tessar_f2.8.dat", "triplet_f2.5.dat", "mori_f2.8.dat",
+                                  "petzval_f1.25.dat"])
+def test_guarded_kolb_all_lenses(port, lens):
+    from zoic_b200.workloads import LENSES, lens_path
+    fnum, focal = LENSES[lens]
+    res, st = _check_guarded(dict(lensModel=1, lensDataPath=lens_path(lens), focalLength=focal, fStop=fnum), port)
+    assert st["exact_reruns"] < 0.02 * st["rays"]
+
+
+def test_guarded_kolb_no_lut_and_bokeh(port):
+    from zoic_b200.synth import hex_bokeh_image
+    from zoic_b200.workloads import lens_path
+    _check_guarded(dict(lensModel=1, lensDataPath=lens_path("double_gauss_f2.0.dat"), focalLength=5.0, fStop=2.0,
+                        kolbSamplingLUT=0), port, n=100_000)
+    _check_guarded(dict(lensModel=1, lensDataPath=lens_path("double_gauss_f2.0.dat"), focalLength=5.0, fStop=2.8,
+                        useImage=1, exposureControl=0.3), port, n=100_000, image=hex_bokeh_image(255))
+
+
+def test_guarded_thin_lens(port):
+    from zoic_b200.synth import hex_bokeh_image
+    _check_guarded(dict(lensModel=0, focalLength=3.5, fStop=2.8, opticalVignettingDistance=2.0), port)
+    _check_guarded(dict(lensModel=0, focalLength=3.5, fStop=2.8, opticalVignettingDistance=2.0, useImage=1), port,
+                   image=hex_bokeh_image(255))

@@ -91,6 +91,10 @@ class ZoicCamera:
     def set_mode(self, mode):
         capi.check(self.lib.zoicb_set_mode(self.ctx, int(mode)))
 
+    def set_guard_scale(self, scale):
+        """Validation hook: scale the decision margins of the guarded mode (1 = shipped, 0 = none)."""
+        capi.check(self.lib.zoicb_set_guard_scale(self.ctx, float(scale)))
+
     @property
     def mode(self):
         return self.lib.zoicb_get_mode(self.ctx)

@@ -25,8 +25,11 @@ struct Element {
     float eta2;       // fl(eta*eta)
     float inv_radius; // fl(1/R)       (fast path only)
     int32_t tir_possible;  // ior_i > ior_next (src/zoic.cpp:1019)
-    float rim2_guard;      // fast path: |h2 - rim2| below this => undecided
-    float pad0, pad1;
+    // guarded fast path: a rim test whose margin |h2 - rim2| is below
+    //   rim2_guard + dt_guard * |hit.xy . dir.xy|   is "undecided" and the ray is re-run exactly
+    float rim2_guard;      // relative part: accumulated fp32 drift of the ray state
+    float dt_guard;        // 2 * (largest plausible error of the reference's own ray parameter t at this surface)
+    float vertex;          // z of the surface vertex on the axis (= center + radius, from the thickness sums)
 };
 
 struct LensState {
@@ -52,7 +55,7 @@ struct ThinState {
     float ov_radius_true;   // fl(apertureRadius * opticalVignettingRadius), src/zoic.cpp:1302
     int32_t use_dof;
     int32_t use_ov;         // opticalVignettingDistance > 0
-    int32_t pad;
+    float ov_guard;         // guarded fast path: |hyp - ov_radius_true| below this => undecided
 };
 
 // Image-based aperture sampling tables (device pointers), src/zoic.cpp:117-122
@@ -70,7 +73,7 @@ struct CameraState {
     int32_t lens_model;  // 0 thin lens, 1 raytraced
     int32_t use_image;
     float weight_scale;  // exposure: 1+e^2 (e>0), 1/(1+e^2) (e<0), 1 (src/zoic.cpp:1981-1987)
-    int32_t pad;
+    float guard_scale;   // 1 = shipped decision margins (scales the fixed miss / TIR margins of the fast path)
     ThinState thin;
     BokehTables bokeh;
     LensState lens;

@@ -2,6 +2,7 @@
 #include <cuda_runtime.h>
 
 #include <atomic>
+#include <map>
 #include <cstdio>
 #include <cstring>
 #include <mutex>
@@ -38,7 +39,7 @@ void count_launches(int k) { if (k > 0) g_launches.fetch_add((uint64_t)k, std::m
 
 struct zoicb_ctx {
     int device = 0;
-    int mode = ZOICB_MODE_EXACT;
+    int mode = ZOICB_MODE_GUARDED;
     HostCamera host;
     // device tables (bokeh)
     float* d_cdf_row = nullptr;
@@ -46,6 +47,10 @@ struct zoicb_ctx {
     float* d_cdf_col = nullptr;
     uint16_t* d_rel_col = nullptr;
     DeviceStats* d_stats = nullptr;
+    // guarded-mode scratch, one per stream the caller uses (stream order serialises reuse)
+    std::vector<float> base_guards;
+    std::mutex ws_mu;
+    std::map<cudaStream_t, Workspace> workspaces;
     // host-buffer pipeline (zoicb_generate_host)
     static constexpr int kSlots = 3;
     uint64_t chunk = 0;
@@ -89,9 +94,35 @@ bool lut_trace_gpu(void* user, const LensState& lens, const float* film_x, int n
     return ok;
 }
 
+// Scratch for the guarded mode on `st`, large enough for n samples: room for n/64 undecided samples
+// (measured rates are 1e-4 .. 3e-3); anything beyond the capacity is settled inline by the kernel.
+cudaError_t get_workspace(zoicb_ctx* c, cudaStream_t st, uint64_t n, Workspace* out) {
+    std::lock_guard<std::mutex> lock(c->ws_mu);
+    Workspace& w = c->workspaces[st];
+    unsigned long long want = n / 64 + 4096;
+    if (want > (1ull << 27)) want = 1ull << 27;
+    cudaError_t e;
+    if (!w.counters) {
+        if ((e = cudaMalloc(&w.counters, 2 * sizeof(unsigned long long))) != cudaSuccess) return e;
+    }
+    if (w.capacity < want) {
+        if (w.queue) {
+            if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return e;
+            cudaFree(w.queue);
+            w.queue = nullptr;
+            w.capacity = 0;
+        }
+        if ((e = cudaMalloc(&w.queue, want * sizeof(unsigned long long))) != cudaSuccess) return e;
+        w.capacity = want;
+    }
+    *out = w;
+    return cudaSuccess;
+}
+
 void free_ctx(zoicb_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
+    for (auto& kv : c->workspaces) { cudaFree(kv.second.counters); cudaFree(kv.second.queue); }
     cudaFree(c->d_cdf_row); cudaFree(c->d_row_idx); cudaFree(c->d_cdf_col); cudaFree(c->d_rel_col);
     cudaFree(c->d_stats);
     for (int s = 0; s < zoicb_ctx::kSlots; ++s) {
@@ -184,6 +215,24 @@ zoicb_status zoicb_set_mode(zoicb_ctx* ctx, int mode) {
 }
 int zoicb_get_mode(const zoicb_ctx* ctx) { return ctx ? ctx->mode : -1; }
 
+zoicb_status zoicb_set_guard_scale(zoicb_ctx* ctx, float scale) {
+    if (!ctx || !(scale >= 0.0f)) return fail(ZOICB_ERR_INVALID_ARGUMENT, "zoicb_set_guard_scale: bad argument");
+    if (ctx->base_guards.empty()) {
+        for (int i = 0; i < kMaxElements; ++i) {
+            ctx->base_guards.push_back(ctx->host.state.lens.e[i].rim2_guard);
+            ctx->base_guards.push_back(ctx->host.state.lens.e[i].dt_guard);
+        }
+        ctx->base_guards.push_back(ctx->host.state.thin.ov_guard);
+    }
+    for (int i = 0; i < kMaxElements; ++i) {
+        ctx->host.state.lens.e[i].rim2_guard = ctx->base_guards[2 * i] * scale;
+        ctx->host.state.lens.e[i].dt_guard = ctx->base_guards[2 * i + 1] * scale;
+    }
+    ctx->host.state.thin.ov_guard = ctx->base_guards[2 * kMaxElements] * scale;
+    ctx->host.state.guard_scale = scale;
+    return ZOICB_OK;
+}
+
 zoicb_status zoicb_generate(zoicb_ctx* ctx, const void* d_samples, uint64_t n, uint64_t first_index, uint64_t rng_seed,
                             void* d_origin_w, void* d_dir_tries, void* stream) {
     if (!ctx) return fail(ZOICB_ERR_INVALID_ARGUMENT, "zoicb_generate: null context");
@@ -191,8 +240,10 @@ zoicb_status zoicb_generate(zoicb_ctx* ctx, const void* d_samples, uint64_t n, u
     if (!d_samples || !d_origin_w || !d_dir_tries) return fail(ZOICB_ERR_INVALID_ARGUMENT, "zoicb_generate: null buffer");
     ZCUDA(cudaSetDevice(ctx->device), "cudaSetDevice");
     int launches = 0;
+    Workspace ws = {nullptr, nullptr, 0};
+    if (ctx->mode == ZOICB_MODE_GUARDED) ZCUDA(get_workspace(ctx, (cudaStream_t)stream, n, &ws), "workspace");
     cudaError_t e = launch_generate(ctx->host.state, ctx->mode, (const float4*)d_samples, n, first_index, rng_seed,
-                                    (float4*)d_origin_w, (float4*)d_dir_tries, ctx->d_stats, (cudaStream_t)stream, &launches);
+                                    (float4*)d_origin_w, (float4*)d_dir_tries, ctx->d_stats, (cudaStream_t)stream, ws, &launches);
     count_launches(launches);
     if (e != cudaSuccess) return cuda_fail(e, "zoicb_generate launch");
     return ZOICB_OK;
@@ -244,8 +295,10 @@ zoicb_status zoicb_generate_host(zoicb_ctx* ctx, const float* h_samples, uint64_
         const float* src = h_samples + 4 * b;
         if (!direct) { std::memcpy(ctx->h_in[s], src, m * sizeof(float4)); src = (const float*)ctx->h_in[s]; }
         ZCUDA(cudaMemcpyAsync(ctx->d_in[s], src, m * sizeof(float4), cudaMemcpyHostToDevice, ctx->streams[s]), "H2D");
+        Workspace ws = {nullptr, nullptr, 0};
+        if (ctx->mode == ZOICB_MODE_GUARDED) ZCUDA(get_workspace(ctx, ctx->streams[s], m, &ws), "workspace");
         cudaError_t e = launch_generate(ctx->host.state, ctx->mode, ctx->d_in[s], m, first_index + b, rng_seed, ctx->d_o[s],
-                                        ctx->d_d[s], ctx->d_stats, ctx->streams[s], &launches);
+                                        ctx->d_d[s], ctx->d_stats, ctx->streams[s], ws, &launches);
         if (e != cudaSuccess) { count_launches(launches); return cuda_fail(e, "zoicb_generate_host launch"); }
         float* dst_o = direct ? h_origin_w + 4 * b : (float*)ctx->h_o[s];
         float* dst_d = direct ? h_dir_tries + 4 * b : (float*)ctx->h_d[s];

@@ -236,8 +236,12 @@ void pack_elements(const std::vector<LensRow>& rows, int stop, float user_radius
         e.eta2 = xmul(e.eta, e.eta);
         e.inv_radius = 1.0f / e.radius;
         e.tir_possible = rows[i].ior > next_ior ? 1 : 0;
-        e.rim2_guard = 0.0f;
-        e.pad0 = e.pad1 = 0.0f;
+        // guard constants of the fast path: see kernels.cu fast_surface().  The reference computes
+        // t = tca + thc from two numbers of magnitude ~(|R| + path length); its own rounding noise in t is
+        // a few ulps of that magnitude (5e-4 cm at the R = 4967 cm stop), all of it ALONG the ray.
+        e.rim2_guard = 2e-5f * T;
+        e.dt_guard = 2.0f * (8.0f * 5.9604645e-8f * (fabsf(e.radius) + 16.0f));
+        e.vertex = z;
     }
 }
 
@@ -386,6 +390,7 @@ zoicb_status build_camera(const zoicb_params& p, const float* rgb, int w, int h,
     S.use_image = p.useImage ? 1 : 0;
     const float e2 = xmul(p.exposureControl, p.exposureControl);  // :1981-1987
     S.weight_scale = 1.0f;
+    S.guard_scale = 1.0f;
     if (p.exposureControl > 0.0f) S.weight_scale = xadd(1.0f, e2);
     else if (p.exposureControl < 0.0f) S.weight_scale = xdiv(1.0f, xadd(1.0f, e2));
 
@@ -407,6 +412,7 @@ zoicb_status build_camera(const zoicb_params& p, const float* rgb, int w, int h,
         T.ov_radius_true = xmul(C.apertureRadius, p.opticalVignettingRadius);
         T.use_dof = p.useDof ? 1 : 0;
         T.use_ov = p.opticalVignettingDistance > 0.0f ? 1 : 0;
+        T.ov_guard = 2e-5f * T.ov_radius_true;
         return ZOICB_OK;
     }
     if (p.lensModel != ZOICB_RAYTRACED) { *err = "lensModel must be THINLENS (0) or RAYTRACED (1)"; return ZOICB_ERR_INVALID_ARGUMENT; }

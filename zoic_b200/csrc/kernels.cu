@@ -117,132 +117,365 @@ __device__ __forceinline__ void flush_stats(const LocalStats& ls, DeviceStats* g
 }
 
 // ------------------------------------------------------------------------------------------------
-// EXACT thin lens (src/zoic.cpp:1771-1848, :1297-1305)
+// EXACT thin lens, one sample (src/zoic.cpp:1771-1848, :1297-1305)
 // ------------------------------------------------------------------------------------------------
 template <bool kImage>
+__device__ __forceinline__ void thin_exact_sample(const CameraState& cam, const BokehView& bk, float4 s, uint64_t gidx,
+                                                  uint64_t seed, float4* o4, float4* d4, LocalStats& ls) {
+    const ThinState& T = cam.thin;
+    Vec3 p = vmake(xmul(s.x, T.tan_fov), xmul(s.y, T.tan_fov), 1.0f);
+    const Vec3 dir0 = vnormalize(p);  // p - origin0 with origin0 = 0
+    Vec3 origin = vmake(0.0f, 0.0f, 0.0f);
+    Vec3 dir = dir0;
+    int tries = 0;
+    float weight = 1.0f;
+    ls.rays++;
+    ls.attempts++;
+    if (T.use_dof) {
+        float lx, ly;
+        lens_sample<kImage>(bk, s.z, s.w, &lx, &ly);
+        const float inter = fabsf(xdiv(T.focal_distance, dir0.z));
+        const Vec3 focus = vscale(dir0, inter);
+        origin = vmake(xmul(lx, T.aperture_radius), xmul(ly, T.aperture_radius), 0.0f);
+        dir = vnormalize(vsub(focus, origin));
+        if (T.use_ov) {
+            Xor128 rng = sample_stream(seed, gidx);
+            while (tries <= kMaxTries) {
+                // empericalOpticalVignetting
+                float qx = xsub(xmul(dir.x, T.ov_distance), origin.x);
+                float qy = xsub(xmul(dir.y, T.ov_distance), origin.y);
+                float hyp = xsqrt(xadd(xmul(qx, qx), xmul(qy, qy)));
+                if (fabsf(hyp) < T.ov_radius_true) break;
+                float u, v;
+                draw_pair(rng, &u, &v);
+                lens_sample<kImage>(bk, u, v, &lx, &ly);
+                origin = vmake(xmul(lx, T.aperture_radius), xmul(ly, T.aperture_radius), 0.0f);
+                dir = vnormalize(vsub(focus, origin));
+                ++tries;
+                ls.attempts++;
+            }
+        }
+        if (tries > kMaxTries) { weight = 0.0f; ls.vignetted++; }
+        else ls.success++;
+    }
+    dir.z = -dir.z;
+    weight = xmul(weight, cam.weight_scale);
+    *o4 = make_float4(origin.x, origin.y, origin.z, weight);
+    *d4 = make_float4(dir.x, dir.y, dir.z, (float)tries);
+}
+
+// ------------------------------------------------------------------------------------------------
+// EXACT raytraced lens, one sample (src/zoic.cpp:1850-1964, :1099-1158)
+// ------------------------------------------------------------------------------------------------
+struct KolbSampleState {  // per-sample constants of the retry loop
+    float fx, fy;          // film point (z = origin_shift)
+    float max_scale, translation, sn, cs;
+};
+
+// exact per-sample set-up: film point, exit-pupil LUT lookup, rotation (src/zoic.cpp:1853-1855, :1891-1911).
+// kAccurateAtan: theta through the double-precision atan2 the reference calls (bit parity) or atan2f.
+template <bool kLut, bool kAccurateAtan>
+__device__ __forceinline__ KolbSampleState kolb_sample_setup(const LensState& L, float sx, float sy) {
+    KolbSampleState k;
+    k.fx = xmul(sx, L.half_sensor);
+    k.fy = xmul(sy, L.half_sensor);
+    k.max_scale = L.first_aperture;
+    k.translation = 0.0f;
+    k.sn = 0.0f;
+    k.cs = 1.0f;
+    if (kLut) {
+        const float dist = fabsf(xsqrt(xadd(xmul(k.fx, k.fx), xmul(k.fy, k.fy))));
+        lut_lookup(L, dist, &k.max_scale, &k.translation);
+        float theta;
+        if (kAccurateAtan) theta = __double2float_rn(atan2((double)k.fy, (double)k.fx));  // :1899
+        else theta = atan2f(k.fy, k.fx);
+        k.sn = fast_sin(theta);
+        k.cs = fast_cos(theta);
+    }
+    return k;
+}
+
+// direction from the film point to the (scaled, translated, rotated) lens sample.  `retry` selects the
+// reference's retry arithmetic, which adds the translation to BOTH components (:1933 vs :1914).
+template <bool kLut>
+__device__ __forceinline__ Vec3 kolb_aim(const LensState& L, const KolbSampleState& k, float lx, float ly, bool retry) {
+    if (kLut) {
+        float px = xadd(xmul(lx, k.max_scale), k.translation);
+        float py = xmul(ly, k.max_scale);
+        if (retry) py = xadd(py, k.translation);
+        float rx = xsub(xmul(px, k.cs), xmul(py, k.sn));
+        float ry = xadd(xmul(px, k.sn), xmul(py, k.cs));
+        return vmake(xsub(rx, k.fx), xsub(ry, k.fy), L.neg_first_thickness);
+    }
+    return vmake(xsub(xmul(lx, k.max_scale), k.fx), xsub(xmul(ly, k.max_scale), k.fy), L.neg_first_thickness);
+}
+
+template <bool kImage, bool kLut>
+__device__ __forceinline__ void kolb_exact_sample(const CameraState& cam, const BokehView& bk, float4 s, uint64_t gidx,
+                                                  uint64_t seed, float4* o4, float4* d4, LocalStats& ls) {
+    const LensState& L = cam.lens;
+    const KolbSampleState k = kolb_sample_setup<kLut, true>(L, s.x, s.y);
+    float lx, ly;
+    lens_sample<kImage>(bk, s.z, s.w, &lx, &ly);
+    Ray r;
+    r.o = vmake(k.fx, k.fy, L.origin_shift);
+    r.d = kolb_aim<kLut>(L, k, lx, ly, false);
+    int tries = 0;
+    Xor128 rng = sample_stream(seed, gidx);
+    ls.rays++;
+    for (;;) {
+        int visited;
+        const int rc = exact_march(L, r, &visited);
+        ls.attempts++;
+        ls.visits += visited;
+        if (rc == kTir) ls.tir++;
+        if (rc == kPass || tries > kMaxTries) break;
+        float u, v;
+        draw_pair(rng, &u, &v);
+        lens_sample<kImage>(bk, u, v, &lx, &ly);
+        r.o = vmake(k.fx, k.fy, L.origin_shift);
+        r.d = kolb_aim<kLut>(L, k, lx, ly, true);
+        ++tries;
+    }
+    float weight = 1.0f;
+    if (tries > kMaxTries) { weight = 0.0f; ls.vignetted++; }
+    else ls.success++;
+    weight = xmul(weight, cam.weight_scale);
+    // flip to look down -Z (:1960-1961)
+    *o4 = make_float4(-r.o.x, -r.o.y, -r.o.z, weight);
+    *d4 = make_float4(-r.d.x, -r.d.y, -r.d.z, (float)tries);
+}
+
+// ------------------------------------------------------------------------------------------------
+// EXACT kernels: one thread per sample, grid-stride
+// ------------------------------------------------------------------------------------------------
+template <int kModel, bool kImage, bool kLut>
 __global__ void __launch_bounds__(256)
-thin_exact_kernel(const __grid_constant__ CameraState cam, const float4* __restrict__ samples, uint64_t n,
-                  uint64_t first_index, uint64_t seed, float4* __restrict__ origin_w, float4* __restrict__ dir_tries,
-                  DeviceStats* stats, int stage_rows) {
+exact_kernel(const __grid_constant__ CameraState cam, const float4* __restrict__ samples, uint64_t n,
+             uint64_t first_index, uint64_t seed, float4* __restrict__ origin_w, float4* __restrict__ dir_tries,
+             DeviceStats* stats, int stage_rows) {
     extern __shared__ float smem[];
     BokehView bk;
     if (kImage) bk = stage_bokeh(cam, smem, stage_rows != 0);
-    const ThinState& T = cam.thin;
     LocalStats ls = {0, 0, 0, 0, 0, 0, 0};
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         const float4 s = __ldcs(samples + i);
-        Vec3 p = vmake(xmul(s.x, T.tan_fov), xmul(s.y, T.tan_fov), 1.0f);
-        const Vec3 dir0 = vnormalize(p);  // p - origin0 with origin0 = 0
-        Vec3 origin = vmake(0.0f, 0.0f, 0.0f);
-        Vec3 dir = dir0;
-        int tries = 0;
-        float weight = 1.0f;
-        ls.rays++;
-        ls.attempts++;
-        if (T.use_dof) {
-            float lx, ly;
-            lens_sample<kImage>(bk, s.z, s.w, &lx, &ly);
-            const float inter = fabsf(xdiv(T.focal_distance, dir0.z));
-            const Vec3 focus = vscale(dir0, inter);
-            origin = vmake(xmul(lx, T.aperture_radius), xmul(ly, T.aperture_radius), 0.0f);
-            dir = vnormalize(vsub(focus, origin));
-            if (T.use_ov) {
-                Xor128 rng = sample_stream(seed, first_index + i);
-                while (tries <= kMaxTries) {
-                    // empericalOpticalVignetting
-                    float qx = xsub(xmul(dir.x, T.ov_distance), origin.x);
-                    float qy = xsub(xmul(dir.y, T.ov_distance), origin.y);
-                    float hyp = xsqrt(xadd(xmul(qx, qx), xmul(qy, qy)));
-                    if (fabsf(hyp) < T.ov_radius_true) break;
-                    float u, v;
-                    draw_pair(rng, &u, &v);
-                    lens_sample<kImage>(bk, u, v, &lx, &ly);
-                    origin = vmake(xmul(lx, T.aperture_radius), xmul(ly, T.aperture_radius), 0.0f);
-                    dir = vnormalize(vsub(focus, origin));
-                    ++tries;
-                    ls.attempts++;
-                }
-            }
-            if (tries > kMaxTries) { weight = 0.0f; ls.vignetted++; }
-            else ls.success++;
-        }
-        dir.z = -dir.z;
-        weight = xmul(weight, cam.weight_scale);
-        __stcs(origin_w + i, make_float4(origin.x, origin.y, origin.z, weight));
-        __stcs(dir_tries + i, make_float4(dir.x, dir.y, dir.z, (float)tries));
+        float4 o4, d4;
+        if (kModel == 0) thin_exact_sample<kImage>(cam, bk, s, first_index + i, seed, &o4, &d4, ls);
+        else kolb_exact_sample<kImage, kLut>(cam, bk, s, first_index + i, seed, &o4, &d4, ls);
+        __stcs(origin_w + i, o4);
+        __stcs(dir_tries + i, d4);
+    }
+    flush_stats(ls, stats);
+}
+
+// Re-run of the samples the guarded kernels could not decide: one thread per queued sample index.
+template <int kModel, bool kImage, bool kLut>
+__global__ void __launch_bounds__(256)
+rerun_kernel(const __grid_constant__ CameraState cam, const float4* __restrict__ samples, uint64_t first_index,
+             uint64_t seed, float4* __restrict__ origin_w, float4* __restrict__ dir_tries, DeviceStats* stats,
+             int stage_rows, const unsigned long long* __restrict__ queue, const unsigned long long* __restrict__ count,
+             unsigned long long capacity) {
+    extern __shared__ float smem[];
+    BokehView bk;
+    if (kImage) bk = stage_bokeh(cam, smem, stage_rows != 0);
+    LocalStats ls = {0, 0, 0, 0, 0, 0, 0};
+    unsigned long long m = *count;
+    if (m > capacity) m = capacity;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < m; q += stride) {
+        const uint64_t i = queue[q];
+        const float4 s = samples[i];
+        float4 o4, d4;
+        if (kModel == 0) thin_exact_sample<kImage>(cam, bk, s, first_index + i, seed, &o4, &d4, ls);
+        else kolb_exact_sample<kImage, kLut>(cam, bk, s, first_index + i, seed, &o4, &d4, ls);
+        origin_w[i] = o4;
+        dir_tries[i] = d4;
+        ls.reruns++;
     }
     flush_stats(ls, stats);
 }
 
 // ------------------------------------------------------------------------------------------------
-// EXACT raytraced lens (src/zoic.cpp:1850-1964, :1099-1158)
+// GUARDED fast path
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float approx_sqrt(float x) { float r; asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float approx_rcp(float x) { float r; asm("rcp.approx.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float approx_rsqrt(float x) { float r; asm("rsqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+
+enum { kUndecided = 3 };
+
+// One surface with fused arithmetic.  `u` is kept unit length across surfaces (Snell's law maps unit
+// vectors to unit vectors), the intersection uses the cancellation-free root, the normal is (c - hit)/R.
+// Every accept/reject test carries a margin; inside the margin the result is kUndecided.
+__device__ __forceinline__ int fast_surface(const Element& e, Vec3& o, Vec3& u, float gscale) {
+    const float dz = e.vertex - o.z;
+    const float Lz = e.center - o.z;
+    const float b = fmaf(o.x, u.x, o.y * u.y);
+    const float tca = fmaf(Lz, u.z, -b);
+    // C = |o - c|^2 - R^2 without forming the two large squares: (dz - R)^2 - R^2 = dz (dz - 2R)
+    const float C = fmaf(dz, dz - 2.0f * e.radius, fmaf(o.x, o.x, o.y * o.y));
+    const float disc = fmaf(tca, tca, -C);
+    const float tiny = 1e-5f * gscale * e.radius2;
+    if (disc < -tiny) return kBlocked;           // clean miss
+    const float thc = approx_sqrt(fmaxf(disc, 0.0f));
+    const float s = e.sgn * thc;
+    // t = tca + s; when the two terms cancel use the conjugate root C / (tca - s)
+    const float t = (tca * s < 0.0f) ? C * approx_rcp(tca - s) : tca + s;
+    const float hx = fmaf(u.x, t, o.x), hy = fmaf(u.y, t, o.y), hz = fmaf(u.z, t, o.z);
+    const float h2 = fmaf(hx, hx, hy * hy);
+    const float w = fmaf(hx, u.x, hy * u.y);
+    const float margin = h2 - e.rim2;
+    const float guard = fmaf(fabsf(w), e.dt_guard, e.rim2_guard);
+    if (margin > guard) return kBlocked;         // outside the rim / stop (also every grazing hit)
+    if (margin > -guard || disc < tiny) return kUndecided;
+    o = vmake(hx, hy, hz);
+    if (e.eta == 1.0f && !e.tir_possible) return kPass;   // same medium on both sides (the stop): no bending
+    const float nzr = e.center - hz;
+    const float c1 = (w - u.z * nzr) * e.inv_radius;      // -(u . n), n = (c - hit)/R
+    const float cs2 = fmaf(-e.eta2 * c1, c1, e.eta2);
+    if (e.tir_possible) {
+        if (cs2 > 1.0f + 1e-4f * gscale) return kTir;
+        if (cs2 > 1.0f - 1e-4f * gscale) return kUndecided;
+    }
+    const float k = fmaf(e.eta, c1, -approx_sqrt(fabsf(1.0f - cs2)));
+    const float kk = k * e.inv_radius;
+    u = vmake(fmaf(kk, -hx, e.eta * u.x), fmaf(kk, -hy, e.eta * u.y), fmaf(kk, nzr, e.eta * u.z));
+    return kPass;
+}
+
+__device__ __forceinline__ int fast_march(const LensState& L, float gscale, Vec3& o, Vec3 d, Vec3* out_dir, int* visited) {
+    // unit direction: rsqrt + one Newton step
+    const float q = fmaf(d.x, d.x, fmaf(d.y, d.y, d.z * d.z));
+    float y = approx_rsqrt(q);
+    y = y * fmaf(-0.5f * q * y, y, 1.5f);
+    Vec3 u = vmake(d.x * y, d.y * y, d.z * y);
+    int n = 0, rc = kPass;
+    for (int i = 0; i < L.count; ++i) {
+        ++n;
+        rc = fast_surface(L.e[i], o, u, gscale);
+        if (rc != kPass) break;
+    }
+    *visited = n;
+    *out_dir = u;
+    return rc;
+}
+
+// Persistent warps with per-lane ray regeneration: a lane whose sample is finished (passed, exhausted its
+// retries, or was handed to the exact re-run queue) immediately takes the next unprocessed sample of the
+// warp's current chunk, so every lane runs an attempt in every iteration; chunks of kChunk samples are
+// handed out by a global counter.  Outputs go straight to their sample index (sector-merged in L2).
+constexpr int kChunk = 2048;
+
 template <bool kImage, bool kLut>
-__global__ void __launch_bounds__(256)
-kolb_exact_kernel(const __grid_constant__ CameraState cam, const float4* __restrict__ samples, uint64_t n,
-                  uint64_t first_index, uint64_t seed, float4* __restrict__ origin_w, float4* __restrict__ dir_tries,
-                  DeviceStats* stats, int stage_rows) {
+__global__ void __launch_bounds__(256, 3)
+kolb_guarded_kernel(const __grid_constant__ CameraState cam, const float4* __restrict__ samples, uint64_t n,
+                    uint64_t first_index, uint64_t seed, float4* __restrict__ origin_w, float4* __restrict__ dir_tries,
+                    DeviceStats* stats, int stage_rows, unsigned long long* chunk_counter, unsigned long long* queue,
+                    unsigned long long* queue_count, unsigned long long capacity) {
     extern __shared__ float smem[];
     BokehView bk;
     if (kImage) bk = stage_bokeh(cam, smem, stage_rows != 0);
     const LensState& L = cam.lens;
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
     LocalStats ls = {0, 0, 0, 0, 0, 0, 0};
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const float4 s = __ldcs(samples + i);
-        const Vec3 film = vmake(xmul(s.x, L.half_sensor), xmul(s.y, L.half_sensor), L.origin_shift);  // :1853-1855
-        float lx, ly;
-        lens_sample<kImage>(bk, s.z, s.w, &lx, &ly);
-        float max_scale = L.first_aperture, translation = 0.0f, sn = 0.0f, cs = 1.0f;
-        Ray r;
-        r.o = film;
-        if (kLut) {
-            const float dist = fabsf(xsqrt(xadd(xmul(film.x, film.x), xmul(film.y, film.y))));
-            lut_lookup(L, dist, &max_scale, &translation);
-            const float theta = __double2float_rn(atan2((double)film.y, (double)film.x));  // :1899
-            sn = fast_sin(theta);
-            cs = fast_cos(theta);
-            float px = xadd(xmul(lx, max_scale), translation);  // :1913-1914 (translation on x only)
-            float py = xmul(ly, max_scale);
-            float rx = xsub(xmul(px, cs), xmul(py, sn));
-            float ry = xadd(xmul(px, sn), xmul(py, cs));
-            r.d = vmake(xsub(rx, film.x), xsub(ry, film.y), L.neg_first_thickness);
-        } else {
-            r.d = vmake(xsub(xmul(lx, max_scale), film.x), xsub(xmul(ly, max_scale), film.y), L.neg_first_thickness);
-        }
-        int tries = 0;
-        Xor128 rng = sample_stream(seed, first_index + i);
-        ls.rays++;
-        for (;;) {
-            int visited;
-            const int rc = exact_march(L, r, &visited);
-            ls.attempts++;
-            ls.visits += visited;
-            if (rc == kTir) ls.tir++;
-            if (rc == kPass || tries > kMaxTries) break;
-            float u, v;
-            draw_pair(rng, &u, &v);
-            lens_sample<kImage>(bk, u, v, &lx, &ly);
-            r.o = film;
-            if (kLut) {
-                float px = xadd(xmul(lx, max_scale), translation);  // :1932-1933 (scalar += on BOTH components)
-                float py = xadd(xmul(ly, max_scale), translation);
-                float rx = xsub(xmul(px, cs), xmul(py, sn));
-                float ry = xadd(xmul(px, sn), xmul(py, cs));
-                r.d = vmake(xsub(rx, film.x), xsub(ry, film.y), L.neg_first_thickness);
-            } else {
-                r.d = vmake(xsub(xmul(lx, max_scale), film.x), xsub(xmul(ly, max_scale), film.y), L.neg_first_thickness);
+    uint64_t cur = 0, end = 0;  // warp-uniform cursor over the current chunk
+    bool exhausted = false;     // warp-uniform: the global counter ran past n
+    bool have = false;
+    uint64_t idx = 0;
+    KolbSampleState k;
+    k.fx = k.fy = k.max_scale = k.translation = k.sn = 0.0f; k.cs = 1.0f;
+    Xor128 rng = {0, 0, 0, 0};
+    int tries = 0;
+    unsigned s_attempts = 0, s_visits = 0, s_tir = 0;  // counters of the sample in flight
+    float lx = 0.0f, ly = 0.0f;
+
+    for (;;) {
+        // ---- regeneration
+        const unsigned need = __ballot_sync(0xffffffffu, !have);
+        if (need) {
+            if (cur == end && !exhausted) {
+                unsigned long long base = 0;
+                if (lane == 0) base = atomicAdd(chunk_counter, (unsigned long long)kChunk);
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (base >= n) { exhausted = true; }
+                else { cur = base; end = (base + kChunk < n) ? base + kChunk : n; }
             }
-            ++tries;
+            const unsigned avail = (unsigned)(end - cur);
+            const unsigned want = __popc(need);
+            const unsigned take = want < avail ? want : avail;
+            const unsigned rank = __popc(need & lt_mask);
+            if (!have && rank < take) {
+                idx = cur + rank;
+                const float4 s = __ldcs(samples + idx);
+                k = kolb_sample_setup<kLut, false>(L, s.x, s.y);
+                lens_sample<kImage>(bk, s.z, s.w, &lx, &ly);
+                tries = 0;
+                s_attempts = s_visits = s_tir = 0;
+                have = true;
+            }
+            cur += take;
         }
-        float weight = 1.0f;
-        if (tries > kMaxTries) { weight = 0.0f; ls.vignetted++; }
-        else ls.success++;
-        weight = xmul(weight, cam.weight_scale);
-        // flip to look down -Z (:1960-1961)
-        __stcs(origin_w + i, make_float4(-r.o.x, -r.o.y, -r.o.z, weight));
-        __stcs(dir_tries + i, make_float4(-r.d.x, -r.d.y, -r.d.z, (float)tries));
+        const unsigned active = __ballot_sync(0xffffffffu, have);
+        if (!active) {
+            if (exhausted) break;
+            continue;
+        }
+        // ---- one attempt per lane
+        int rc = kBlocked, visited = 0;
+        Vec3 o = vmake(k.fx, k.fy, L.origin_shift), u = vmake(0.0f, 0.0f, 1.0f);
+        if (have) {
+            const Vec3 d = kolb_aim<kLut>(L, k, lx, ly, tries > 0);
+            rc = fast_march(L, cam.guard_scale, o, d, &u, &visited);
+            s_attempts++;
+            s_visits += visited;
+            if (rc == kTir) s_tir++;
+        }
+        // ---- outcome
+        const bool undecided = have && rc == kUndecided;
+        const unsigned umask = __ballot_sync(0xffffffffu, undecided);
+        if (umask) {
+            unsigned long long base = 0;
+            const int leader = __ffs(umask) - 1;
+            if ((int)lane == leader) base = atomicAdd(queue_count, (unsigned long long)__popc(umask));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (undecided) {
+                const unsigned long long pos = base + __popc(umask & lt_mask);
+                if (pos < capacity) {
+                    queue[pos] = idx;
+                } else {  // queue full: settle it here, exactly
+                    float4 o4, d4;
+                    kolb_exact_sample<kImage, kLut>(cam, bk, samples[idx], first_index + idx, seed, &o4, &d4, ls);
+                    __stcs(origin_w + idx, o4);
+                    __stcs(dir_tries + idx, d4);
+                    ls.reruns++;
+                }
+                have = false;
+            }
+        }
+        if (have) {
+            if (rc == kPass || tries > kMaxTries) {
+                float weight = 1.0f;
+                if (tries > kMaxTries) { weight = 0.0f; ls.vignetted++; }
+                else ls.success++;
+                weight *= cam.weight_scale;
+                __stcs(origin_w + idx, make_float4(-o.x, -o.y, -o.z, weight));
+                __stcs(dir_tries + idx, make_float4(-u.x, -u.y, -u.z, (float)tries));
+                ls.rays++;
+                ls.attempts += s_attempts;
+                ls.visits += s_visits;
+                ls.tir += s_tir;
+                have = false;
+            } else {
+                if (tries == 0) rng = sample_stream(seed, first_index + idx);
+                float a, b;
+                draw_pair(rng, &a, &b);
+                lens_sample<kImage>(bk, a, b, &lx, &ly);
+                ++tries;
+            }
+        }
     }
     flush_stats(ls, stats);
 }
@@ -333,12 +566,33 @@ static unsigned grid_for(uint64_t n, int threads, int ctas_per_sm) {
     return (unsigned)(want < cap ? (want ? want : 1) : cap);
 }
 
+template <int kModel, bool kImage, bool kLut>
+static cudaError_t launch_variant(const CameraState& cam, int mode, const float4* samples, uint64_t n, uint64_t first_index,
+                                  uint64_t seed, float4* origin_w, float4* dir_tries, DeviceStats* stats, cudaStream_t st,
+                                  const Workspace& ws, size_t smem, int stage, int* launches) {
+    const int threads = 256;
+    if (mode == 1 && kModel == 1) {  // guarded fast path + exact re-run of the undecided samples
+        cudaError_t e = cudaMemsetAsync(ws.counters, 0, 2 * sizeof(unsigned long long), st);
+        if (e != cudaSuccess) return e;
+        const unsigned grid = (unsigned)sm_count() * 3;  // persistent: 3 CTAs of 8 warps per SM
+        kolb_guarded_kernel<kImage, kLut><<<grid, threads, smem, st>>>(cam, samples, n, first_index, seed, origin_w, dir_tries,
+                                                                      stats, stage, ws.counters, ws.queue, ws.counters + 1,
+                                                                      ws.capacity);
+        rerun_kernel<kModel, kImage, kLut><<<(unsigned)sm_count() * 2, threads, smem, st>>>(
+            cam, samples, first_index, seed, origin_w, dir_tries, stats, stage, ws.queue, ws.counters + 1, ws.capacity);
+        if (launches) *launches += 2;
+        return cudaGetLastError();
+    }
+    exact_kernel<kModel, kImage, kLut><<<grid_for(n, threads, 8), threads, smem, st>>>(cam, samples, n, first_index, seed,
+                                                                                     origin_w, dir_tries, stats, stage);
+    if (launches) *launches += 1;
+    return cudaGetLastError();
+}
+
 cudaError_t launch_generate(const CameraState& cam, int mode, const float4* samples, uint64_t n, uint64_t first_index,
                             uint64_t seed, float4* origin_w, float4* dir_tries, DeviceStats* stats, cudaStream_t st,
-                            int* launches) {
+                            const Workspace& ws, int* launches) {
     if (n == 0) return cudaSuccess;
-    (void)mode;
-    const int threads = 256;
     const bool image = cam.use_image != 0;
     size_t smem = 0;
     int stage = 0;
@@ -346,19 +600,12 @@ cudaError_t launch_generate(const CameraState& cam, int mode, const float4* samp
         size_t need = (size_t)cam.bokeh.h * 8;
         if (need <= 40 * 1024) { smem = need; stage = 1; }
     }
-    const unsigned grid = grid_for(n, threads, 8);
-    if (cam.lens_model == 0) {
-        if (image) thin_exact_kernel<true><<<grid, threads, smem, st>>>(cam, samples, n, first_index, seed, origin_w, dir_tries, stats, stage);
-        else thin_exact_kernel<false><<<grid, threads, 0, st>>>(cam, samples, n, first_index, seed, origin_w, dir_tries, stats, 0);
-    } else {
-        const bool lut = cam.lens.use_lut != 0;
-        if (image && lut) kolb_exact_kernel<true, true><<<grid, threads, smem, st>>>(cam, samples, n, first_index, seed, origin_w, dir_tries, stats, stage);
-        else if (image) kolb_exact_kernel<true, false><<<grid, threads, smem, st>>>(cam, samples, n, first_index, seed, origin_w, dir_tries, stats, stage);
-        else if (lut) kolb_exact_kernel<false, true><<<grid, threads, 0, st>>>(cam, samples, n, first_index, seed, origin_w, dir_tries, stats, 0);
-        else kolb_exact_kernel<false, false><<<grid, threads, 0, st>>>(cam, samples, n, first_index, seed, origin_w, dir_tries, stats, 0);
-    }
-    if (launches) *launches += 1;
-    return cudaGetLastError();
+#define ZL(M, I, U) launch_variant<M, I, U>(cam, mode, samples, n, first_index, seed, origin_w, dir_tries, stats, st, ws, smem, stage, launches)
+    if (cam.lens_model == 0) return image ? ZL(0, true, false) : ZL(0, false, false);
+    const bool lut = cam.lens.use_lut != 0;
+    if (image) return lut ? ZL(1, true, true) : ZL(1, true, false);
+    return lut ? ZL(1, false, true) : ZL(1, false, false);
+#undef ZL
 }
 
 cudaError_t launch_synth(uint32_t W, uint32_t H, uint32_t spp, uint64_t seed, uint64_t first_index, uint64_t n,

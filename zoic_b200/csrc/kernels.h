@@ -7,9 +7,17 @@
 
 namespace zoicb {
 
+// Per-stream scratch of the guarded mode: counters[0] = chunk cursor, counters[1] = number of queued
+// (undecided) sample indices, queue[capacity] = those indices.
+struct Workspace {
+    unsigned long long* counters;
+    unsigned long long* queue;
+    unsigned long long capacity;
+};
+
 cudaError_t launch_generate(const CameraState& cam, int mode, const float4* samples, uint64_t n, uint64_t first_index,
                             uint64_t seed, float4* origin_w, float4* dir_tries, DeviceStats* stats, cudaStream_t st,
-                            int* launches);
+                            const Workspace& ws, int* launches);
 cudaError_t launch_synth(uint32_t W, uint32_t H, uint32_t spp, uint64_t seed, uint64_t first_index, uint64_t n,
                          float4* out, cudaStream_t st, int* launches);
 cudaError_t launch_lut_trace(const LensState& L, const float* d_film_x, int n_film, int per_film, const uint32_t* d_draws,
