@@ -50,7 +50,10 @@ def run(name, wl, n, first, scales):
         res["scales"][str(sc)] = {"path_flips": flips, "out_of_tolerance": bad, "max_rel_origin_err": eo,
                                   "max_dir_err": ed, "exact_reruns": st["exact_reruns"],
                                   "rerun_fraction": st["exact_reruns"] / n, "counters_equal_exact": same_stats}
-        print(name, "scale", sc, res["scales"][str(sc)], flush=True)
+        r = res["scales"][str(sc)]
+        print("%-34s first %-12d scale %-5g flips %-6d bad %-3d err_o %.2e err_d %.2e rerun %.2e stats_eq %s" % (
+            name, first, sc, r["path_flips"], r["out_of_tolerance"], r["max_rel_origin_err"], r["max_dir_err"],
+            r["rerun_fraction"], r["counters_equal_exact"]), flush=True)
     cam.close()
     return res
 
@@ -59,7 +62,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--samples", type=int, default=1 << 26)
     ap.add_argument("--out", default="")
-    ap.add_argument("--scales", default="1,0.25,0.05,0")
+    ap.add_argument("--scales", default="1,0.5,0.25,0.1,0")
     a = ap.parse_args()
     scales = [float(x) for x in a.scales.split(",")]
     out = []

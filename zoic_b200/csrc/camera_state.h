@@ -29,7 +29,10 @@ struct Element {
     //   rim2_guard + dt_guard * |hit.xy . dir.xy|   is "undecided" and the ray is re-run exactly
     float rim2_guard;      // relative part: accumulated fp32 drift of the ray state
     float dt_guard;        // 2 * (largest plausible error of the reference's own ray parameter t at this surface)
-    float vertex;          // z of the surface vertex on the axis (= center + radius, from the thickness sums)
+    float vertex;          // z where the sphere the REFERENCE intersects (centre fl(z - R), radius^2 fl(R*R))
+                           // crosses the axis: fl(center + R)
+    float r2_corr;         // R*R - fl(R*R) evaluated in double: |o-c|^2 - radius2 = dz*(dz-2R) + ox^2+oy^2 + r2_corr
+    float pad0, pad1, pad2;
 };
 
 struct LensState {

@@ -209,7 +209,7 @@ float image_distance(const std::vector<LensRow>& rows, float object_distance) {
 }
 
 // ------------------------------------------------------------------ kernel-facing element constants
-void pack_elements(const std::vector<LensRow>& rows, int stop, float user_radius, LensState* L) {
+void pack_elements(const std::vector<LensRow>& rows, int stop, float user_radius, float origin_shift, LensState* L) {
     const int n = (int)rows.size();
     L->count = n;
     L->aperture_element = stop;
@@ -236,12 +236,18 @@ void pack_elements(const std::vector<LensRow>& rows, int stop, float user_radius
         e.eta2 = xmul(e.eta, e.eta);
         e.inv_radius = 1.0f / e.radius;
         e.tir_possible = rows[i].ior > next_ior ? 1 : 0;
-        // guard constants of the fast path: see kernels.cu fast_surface().  The reference computes
-        // t = tca + thc from two numbers of magnitude ~(|R| + path length); its own rounding noise in t is
-        // a few ulps of that magnitude (5e-4 cm at the R = 4967 cm stop), all of it ALONG the ray.
-        e.rim2_guard = 2e-5f * T;
-        e.dt_guard = 2.0f * (8.0f * 5.9604645e-8f * (fabsf(e.radius) + 16.0f));
-        e.vertex = z;
+        // Fast-path constants (kernels.cu fast_surface()).  The fast path intersects the very sphere the
+        // reference does -- centre fl(z - R), squared radius fl(R*R) -- but through a cancellation-free form.
+        e.vertex = (float)((double)e.center + (double)e.radius);
+        e.r2_corr = (float)((double)e.radius * (double)e.radius - (double)e.radius2);
+        // Decision margins.  (1) The reference forms t = tca + thc from numbers of magnitude |o - c| <= |R| + len;
+        // a rounding analysis of its operation sequence bounds the error of t by ~4.9 ulp of that magnitude
+        // (2.4e-3 cm at the R = 4967 cm stop), all of it ALONG the ray, which moves hx^2+hy^2 by 2*(h.u_xy)*dt.
+        // (2) Direction noise of ~2e-7 rad per surface displaces later hits by a few 1e-6 cm.
+        const float len = fabsf(origin_shift) + 1.0f;
+        e.dt_guard = 2.0f * (8.0f * 5.9604645e-8f * (fabsf(e.radius) + len));
+        e.rim2_guard = 2.0f * sqrtf(T) * (4e-6f * fmaxf(len, 2.0f));
+        e.pad0 = e.pad1 = e.pad2 = 0.0f;
     }
 }
 
@@ -442,7 +448,7 @@ zoicb_status build_camera(const zoicb_params& p, const float* rgb, int w, int h,
     for (int i = 0; i <= stop; ++i) stop_z = xadd(stop_z, rows[i].thickness);
 
     LensState& L = S.lens;
-    pack_elements(rows, stop, user_radius, &L);
+    pack_elements(rows, stop, user_radius, shift, &L);
     L.origin_shift = shift;
     L.half_sensor = (float)((double)p.sensorWidth * 0.5);
     L.first_aperture = rows[0].aperture;

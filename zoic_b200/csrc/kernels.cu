@@ -315,7 +315,7 @@ __device__ __forceinline__ int fast_surface(const Element& e, Vec3& o, Vec3& u, 
     const float b = fmaf(o.x, u.x, o.y * u.y);
     const float tca = fmaf(Lz, u.z, -b);
     // C = |o - c|^2 - R^2 without forming the two large squares: (dz - R)^2 - R^2 = dz (dz - 2R)
-    const float C = fmaf(dz, dz - 2.0f * e.radius, fmaf(o.x, o.x, o.y * o.y));
+    const float C = fmaf(dz, dz - 2.0f * e.radius, fmaf(o.x, o.x, o.y * o.y)) + e.r2_corr;
     const float disc = fmaf(tca, tca, -C);
     const float tiny = 1e-5f * gscale * e.radius2;
     if (disc < -tiny) return kBlocked;           // clean miss
