@@ -300,66 +300,108 @@ rerun_kernel(const __grid_constant__ CameraState cam, const float4* __restrict__
 // ------------------------------------------------------------------------------------------------
 // GUARDED fast path
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float approx_sqrt(float x) { float r; asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
-__device__ __forceinline__ float approx_rcp(float x) { float r; asm("rcp.approx.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
-__device__ __forceinline__ float approx_rsqrt(float x) { float r; asm("rsqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float approx_sqrt(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float approx_rcp(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float approx_rsqrt(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 
 enum { kUndecided = 3 };
 
-// One surface with fused arithmetic.  `u` is kept unit length across surfaces (Snell's law maps unit
-// vectors to unit vectors), the intersection uses the cancellation-free root, the normal is (c - hit)/R.
-// Every accept/reject test carries a margin; inside the margin the result is kUndecided.
-__device__ __forceinline__ int fast_surface(const Element& e, Vec3& o, Vec3& u, float gscale) {
-    const float dz = e.vertex - o.z;
-    const float Lz = e.center - o.z;
-    const float b = fmaf(o.x, u.x, o.y * u.y);
-    const float tca = fmaf(Lz, u.z, -b);
-    // C = |o - c|^2 - R^2 without forming the two large squares: (dz - R)^2 - R^2 = dz (dz - 2R)
-    const float C = fmaf(dz, dz - 2.0f * e.radius, fmaf(o.x, o.x, o.y * o.y)) + e.r2_corr;
-    const float disc = fmaf(tca, tca, -C);
-    const float tiny = 1e-5f * gscale * e.radius2;
-    if (disc < -tiny) return kBlocked;           // clean miss
-    const float thc = approx_sqrt(fmaxf(disc, 0.0f));
-    const float s = e.sgn * thc;
-    // t = tca + s; when the two terms cancel use the conjugate root C / (tca - s)
-    const float t = (tca * s < 0.0f) ? C * approx_rcp(tca - s) : tca + s;
-    const float hx = fmaf(u.x, t, o.x), hy = fmaf(u.y, t, o.y), hz = fmaf(u.z, t, o.z);
-    const float h2 = fmaf(hx, hx, hy * hy);
-    const float w = fmaf(hx, u.x, hy * u.y);
-    const float margin = h2 - e.rim2;
-    const float guard = fmaf(fabsf(w), e.dt_guard, e.rim2_guard);
-    if (margin > guard) return kBlocked;         // outside the rim / stop (also every grazing hit)
-    if (margin > -guard || disc < tiny) return kUndecided;
-    o = vmake(hx, hy, hz);
-    if (e.eta == 1.0f && !e.tir_possible) return kPass;   // same medium on both sides (the stop): no bending
-    const float nzr = e.center - hz;
-    const float c1 = (w - u.z * nzr) * e.inv_radius;      // -(u . n), n = (c - hit)/R
-    const float cs2 = fmaf(-e.eta2 * c1, c1, e.eta2);
-    if (e.tir_possible) {
-        if (cs2 > 1.0f + 1e-4f * gscale) return kTir;
-        if (cs2 > 1.0f - 1e-4f * gscale) return kUndecided;
-    }
-    const float k = fmaf(e.eta, c1, -approx_sqrt(fabsf(1.0f - cs2)));
-    const float kk = k * e.inv_radius;
-    u = vmake(fmaf(kk, -hx, e.eta * u.x), fmaf(kk, -hy, e.eta * u.y), fmaf(kk, nzr, e.eta * u.z));
-    return kPass;
-}
-
-__device__ __forceinline__ int fast_march(const LensState& L, float gscale, Vec3& o, Vec3 d, Vec3* out_dir, int* visited) {
+// The element stack with fused arithmetic (one function so that the compiler sees straight-line code).
+// `u` is kept unit length across surfaces (Snell's law maps unit vectors to unit vectors), the intersection
+// uses the cancellation-free root of the quadratic, the normal is (c - hit)/R, and the refraction is
+// computed unconditionally (eta = 1 at the stop gives u' = u up to 1e-8).  Every accept/reject test carries
+// a margin; inside the margin the result is kUndecided.  A lane leaves the stack at the surface that stops
+// it, holding the state the reference would hold there (o, u of the last completed surface; the raw aim
+// vector if the very first surface stops it; the new origin if it is total internal reflection).
+//
+// kN > 0: compile-time element count, fully unrolled, element constants become immediate operands;
+// kN == 0: run-time count.
+template <int kN>
+__device__ __forceinline__ int fast_march(const LensState& L, float gscale, Vec3& o, Vec3& u, int* visited) {
+    float ox = o.x, oy = o.y, oz = o.z;
+    const float dx = u.x, dy = u.y, dz0 = u.z;
     // unit direction: rsqrt + one Newton step
-    const float q = fmaf(d.x, d.x, fmaf(d.y, d.y, d.z * d.z));
+    const float q = fmaf(dx, dx, fmaf(dy, dy, dz0 * dz0));
     float y = approx_rsqrt(q);
     y = y * fmaf(-0.5f * q * y, y, 1.5f);
-    Vec3 u = vmake(d.x * y, d.y * y, d.z * y);
+    float ux = dx * y, uy = dy * y, uz = dz0 * y;
+    const float tir_hi = fmaf(1e-4f, gscale, 1.0f), tir_lo = fmaf(-1e-4f, gscale, 1.0f);
     int n = 0, rc = kPass;
-    for (int i = 0; i < L.count; ++i) {
+    const int count = kN > 0 ? kN : L.count;
+#pragma unroll
+    for (int i = 0; i < (kN > 0 ? kN : kMaxElements); ++i) {
+        if (kN == 0 && i >= count) break;
+        const Element& e = L.e[i];
         ++n;
-        rc = fast_surface(L.e[i], o, u, gscale);
-        if (rc != kPass) break;
+        const float dz = e.vertex - oz;
+        const float Lz = e.center - oz;
+        const float b = fmaf(ox, ux, oy * uy);
+        const float tca = fmaf(Lz, uz, -b);
+        // C = |o - c|^2 - radius2 without forming the two large squares: (dz - R)^2 - R^2 = dz (dz - 2R)
+        const float C = fmaf(dz, dz - 2.0f * e.radius, fmaf(ox, ox, oy * oy)) + e.r2_corr;
+        const float disc = fmaf(tca, tca, -C);
+        const float tiny = 1e-5f * gscale * e.radius2;
+        const float s = e.sgn * approx_sqrt(fmaxf(disc, 0.0f));
+        // t = tca + s; when the two terms cancel use the conjugate root C / (tca - s)
+        const float t_conj = C * approx_rcp(tca - s);
+        const float t = (tca * s < 0.0f) ? t_conj : tca + s;
+        const float hx = fmaf(ux, t, ox), hy = fmaf(uy, t, oy), hz = fmaf(uz, t, oz);
+        const float h2 = fmaf(hx, hx, hy * hy);
+        const float w = fmaf(hx, ux, hy * uy);
+        const float margin = h2 - e.rim2;
+        const float guard = fmaf(fabsf(w), e.dt_guard, e.rim2_guard);
+        // clean miss, or outside the rim / stop (every grazing hit lands far outside the rim)
+        const bool blocked = (disc < -tiny) || (margin > guard);
+        const bool unsure = (margin > -guard) || (disc < tiny);
+        if (blocked || unsure) {
+            rc = blocked ? kBlocked : kUndecided;
+            if (i == 0) { ux = dx; uy = dy; uz = dz0; }
+            break;
+        }
+        const float nzr = e.center - hz;
+        const float c1 = (w - uz * nzr) * e.inv_radius;       // -(u . n), n = (c - hit)/R
+        const float cs2 = fmaf(-e.eta2 * c1, c1, e.eta2);     // <= eta^2: can exceed 1 only where ior_i > ior_next
+        const float k = fmaf(e.eta, c1, -approx_sqrt(fabsf(1.0f - cs2)));
+        const float kk = k * e.inv_radius;
+        ox = hx; oy = hy; oz = hz;                             // the reference moves the origin before Snell (:1130)
+        if (cs2 > tir_lo) {
+            rc = cs2 > tir_hi ? kTir : kUndecided;
+            if (i == 0) { ux = dx; uy = dy; uz = dz0; }
+            break;
+        }
+        ux = fmaf(kk, -hx, e.eta * ux);
+        uy = fmaf(kk, -hy, e.eta * uy);
+        uz = fmaf(kk, nzr, e.eta * uz);
     }
+    o = vmake(ox, oy, oz);
+    u = vmake(ux, uy, uz);
     *visited = n;
-    *out_dir = u;
     return rc;
+}
+
+// approximate-division variant of the concentric map (same branch decisions: a, b are computed exactly)
+__device__ __forceinline__ void concentric_disk_fast(float ox, float oy, float* lx, float* ly) {
+    const float a = two_x_minus_one(ox);
+    const float b = two_x_minus_one(oy);
+    const bool first = xmul(a, a) > xmul(b, b);
+    const float num = first ? b : a, den = first ? a : b;
+    const float qt = num * approx_rcp(den);
+    const float r = first ? a : b;
+    const float phi = first ? 0.78539816339f * qt : 1.57079632679489661923f - 0.78539816339f * qt;
+    // phi in [-pi/4, 3pi/4]: phi + pi < 2pi always; (phi + pi/2) + pi may pass 2pi once
+    const float two_pi = ZOICB_PI_F * 2.0f;
+    const float xs = xsub(xadd(phi, ZOICB_PI_F), ZOICB_PI_F);
+    float vc = xadd(xadd(phi, ZOICB_PI_F * 0.5f), ZOICB_PI_F);
+    vc = vc >= two_pi ? xsub(vc, two_pi) : vc;
+    const float xc = xsub(vc, ZOICB_PI_F);
+    *lx = r * parabola_sin(xc);
+    *ly = r * parabola_sin(xs);
+}
+
+template <bool kImage>
+__device__ __forceinline__ void lens_sample_fast(const BokehView& b, float u, float v, float* lx, float* ly) {
+    if (kImage) bokeh_sample(b, u, v, lx, ly);
+    else concentric_disk_fast(u, v, lx, ly);
 }
 
 // Persistent warps with per-lane ray regeneration: a lane whose sample is finished (passed, exhausted its
@@ -368,7 +410,7 @@ __device__ __forceinline__ int fast_march(const LensState& L, float gscale, Vec3
 // handed out by a global counter.  Outputs go straight to their sample index (sector-merged in L2).
 constexpr int kChunk = 2048;
 
-template <bool kImage, bool kLut>
+template <int kN, bool kImage, bool kLut>
 __global__ void __launch_bounds__(256, 3)
 kolb_guarded_kernel(const __grid_constant__ CameraState cam, const float4* __restrict__ samples, uint64_t n,
                     uint64_t first_index, uint64_t seed, float4* __restrict__ origin_w, float4* __restrict__ dir_tries,
@@ -383,17 +425,18 @@ kolb_guarded_kernel(const __grid_constant__ CameraState cam, const float4* __res
     LocalStats ls = {0, 0, 0, 0, 0, 0, 0};
     uint64_t cur = 0, end = 0;  // warp-uniform cursor over the current chunk
     bool exhausted = false;     // warp-uniform: the global counter ran past n
-    bool have = false;
+    bool have = false;          // this lane holds a sample
+    bool fresh = false;         // ... whose first attempt has not run yet
     uint64_t idx = 0;
     KolbSampleState k;
     k.fx = k.fy = k.max_scale = k.translation = k.sn = 0.0f; k.cs = 1.0f;
     Xor128 rng = {0, 0, 0, 0};
     int tries = 0;
     unsigned s_attempts = 0, s_visits = 0, s_tir = 0;  // counters of the sample in flight
-    float lx = 0.0f, ly = 0.0f;
+    float ua = 0.0f, ub = 0.0f;                        // unit-square point of the next attempt
 
     for (;;) {
-        // ---- regeneration
+        // ---- phase 1a: lanes without a sample take the next ones of the chunk
         const unsigned need = __ballot_sync(0xffffffffu, !have);
         if (need) {
             if (cur == end && !exhausted) {
@@ -411,29 +454,39 @@ kolb_guarded_kernel(const __grid_constant__ CameraState cam, const float4* __res
                 idx = cur + rank;
                 const float4 s = __ldcs(samples + idx);
                 k = kolb_sample_setup<kLut, false>(L, s.x, s.y);
-                lens_sample<kImage>(bk, s.z, s.w, &lx, &ly);
+                ua = s.z;
+                ub = s.w;
                 tries = 0;
                 s_attempts = s_visits = s_tir = 0;
                 have = true;
+                fresh = true;
             }
             cur += take;
         }
-        const unsigned active = __ballot_sync(0xffffffffu, have);
-        if (!active) {
+        if (!__any_sync(0xffffffffu, have)) {
             if (exhausted) break;
             continue;
         }
-        // ---- one attempt per lane
-        int rc = kBlocked, visited = 0;
-        Vec3 o = vmake(k.fx, k.fy, L.origin_shift), u = vmake(0.0f, 0.0f, 1.0f);
+        // ---- phase 1b: lanes whose last attempt failed draw the next lens point (lazy stream seeding)
+        if (have && !fresh) {
+            if (tries == 0) rng = sample_stream(seed, first_index + idx);
+            draw_pair(rng, &ua, &ub);
+            ++tries;
+        }
+        // ---- phase 2: one attempt per lane, all lanes together
+        float lx, ly;
+        lens_sample_fast<kImage>(bk, ua, ub, &lx, &ly);
+        Vec3 o = vmake(k.fx, k.fy, L.origin_shift);
+        Vec3 u = kolb_aim<kLut>(L, k, lx, ly, !fresh);
+        int visited = 0, rc = kBlocked;
+        if (have) rc = fast_march<kN>(L, cam.guard_scale, o, u, &visited);
+        fresh = false;
+        // ---- phase 3: outcome
         if (have) {
-            const Vec3 d = kolb_aim<kLut>(L, k, lx, ly, tries > 0);
-            rc = fast_march(L, cam.guard_scale, o, d, &u, &visited);
             s_attempts++;
             s_visits += visited;
             if (rc == kTir) s_tir++;
         }
-        // ---- outcome
         const bool undecided = have && rc == kUndecided;
         const unsigned umask = __ballot_sync(0xffffffffu, undecided);
         if (umask) {
@@ -455,26 +508,18 @@ kolb_guarded_kernel(const __grid_constant__ CameraState cam, const float4* __res
                 have = false;
             }
         }
-        if (have) {
-            if (rc == kPass || tries > kMaxTries) {
-                float weight = 1.0f;
-                if (tries > kMaxTries) { weight = 0.0f; ls.vignetted++; }
-                else ls.success++;
-                weight *= cam.weight_scale;
-                __stcs(origin_w + idx, make_float4(-o.x, -o.y, -o.z, weight));
-                __stcs(dir_tries + idx, make_float4(-u.x, -u.y, -u.z, (float)tries));
-                ls.rays++;
-                ls.attempts += s_attempts;
-                ls.visits += s_visits;
-                ls.tir += s_tir;
-                have = false;
-            } else {
-                if (tries == 0) rng = sample_stream(seed, first_index + idx);
-                float a, b;
-                draw_pair(rng, &a, &b);
-                lens_sample<kImage>(bk, a, b, &lx, &ly);
-                ++tries;
-            }
+        if (have && (rc == kPass || tries > kMaxTries)) {
+            float weight = 1.0f;
+            if (tries > kMaxTries) { weight = 0.0f; ls.vignetted++; }
+            else ls.success++;
+            weight *= cam.weight_scale;
+            __stcs(origin_w + idx, make_float4(-o.x, -o.y, -o.z, weight));
+            __stcs(dir_tries + idx, make_float4(-u.x, -u.y, -u.z, (float)tries));
+            ls.rays++;
+            ls.attempts += s_attempts;
+            ls.visits += s_visits;
+            ls.tir += s_tir;
+            have = false;
         }
     }
     flush_stats(ls, stats);
@@ -575,9 +620,18 @@ static cudaError_t launch_variant(const CameraState& cam, int mode, const float4
         cudaError_t e = cudaMemsetAsync(ws.counters, 0, 2 * sizeof(unsigned long long), st);
         if (e != cudaSuccess) return e;
         const unsigned grid = (unsigned)sm_count() * 3;  // persistent: 3 CTAs of 8 warps per SM
-        kolb_guarded_kernel<kImage, kLut><<<grid, threads, smem, st>>>(cam, samples, n, first_index, seed, origin_w, dir_tries,
-                                                                      stats, stage, ws.counters, ws.queue, ws.counters + 1,
-                                                                      ws.capacity);
+#define ZG(N) kolb_guarded_kernel<N, kImage, kLut><<<grid, threads, smem, st>>>(cam, samples, n, first_index, seed, origin_w, \
+                                                                         dir_tries, stats, stage, ws.counters, ws.queue,   \
+                                                                         ws.counters + 1, ws.capacity)
+        switch (cam.lens.count) {  // unrolled instantiations for the element counts of the shipped lens tables
+            case 7: ZG(7); break;
+            case 8: ZG(8); break;
+            case 9: ZG(9); break;
+            case 11: ZG(11); break;
+            case 12: ZG(12); break;
+            default: ZG(0); break;
+        }
+#undef ZG
         rerun_kernel<kModel, kImage, kLut><<<(unsigned)sm_count() * 2, threads, smem, st>>>(
             cam, samples, first_index, seed, origin_w, dir_tries, stats, stage, ws.queue, ws.counters + 1, ws.capacity);
         if (launches) *launches += 2;
