@@ -191,8 +191,23 @@ def test_guarded_kolb_no_lut_and_bokeh(port):
                         useImage=1, exposureControl=0.3), port, n=100_000, image=hex_bokeh_image(255))
 
 
-def test_guarded_thin_lens(port):
+def test_guarded_thin_lens_is_bit_exact(port):
+    """The thin lens has no double-precision step, so its default (persistent-warp) kernel keeps the exact
+    arithmetic: bit-identical to the oracle, only the order of work differs."""
+    from zoic_b200 import ZoicCamera, MODE_GUARDED
     from zoic_b200.synth import hex_bokeh_image
-    _check_guarded(dict(lensModel=0, focalLength=3.5, fStop=2.8, opticalVignettingDistance=2.0), port)
-    _check_guarded(dict(lensModel=0, focalLength=3.5, fStop=2.8, opticalVignettingDistance=2.0, useImage=1), port,
-                   image=hex_bokeh_image(255))
+    for image, kw in [(None, dict(lensModel=0, focalLength=3.5, fStop=2.8, opticalVignettingDistance=2.0)),
+                      (hex_bokeh_image(255), dict(lensModel=0, focalLength=3.5, fStop=2.8, useImage=1,
+                                                  opticalVignettingDistance=2.0, exposureControl=-0.5)),
+                      (None, dict(lensModel=0, focalLength=2.0, fStop=1.4, opticalVignettingDistance=4.0,
+                                  opticalVignettingRadius=0.6))]:   # harsh vignetting: many zero-weight rays
+        cam = ZoicCamera(image=image, **kw)
+        assert cam.mode == MODE_GUARDED
+        ref = port.PortCamera(image=image, **kw)
+        s = random_samples(300_000, seed=31)
+        o, d, st = _run_gpu(cam, s, seed=8, first_index=5)
+        o2, d2, st2 = ref.generate(s, seed=8, first_index=5, nthreads=8)
+        assert bits_equal(o, o2) and bits_equal(d, d2)
+        assert st["attempts"] == st2["attempts"] and st["vignetted"] == st2["vignetted"]
+        cam.close()
+        ref.close()

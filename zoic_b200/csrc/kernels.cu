@@ -526,6 +526,94 @@ kolb_guarded_kernel(const __grid_constant__ CameraState cam, const float4* __res
 }
 
 // ------------------------------------------------------------------------------------------------
+// Thin lens with optical vignetting: the same persistent-warp / per-lane regeneration schedule, EXACT
+// arithmetic (the thin-lens attempt has no double-precision step, so exactness costs little): results are
+// bit-identical to thin_exact_sample, only the order of work differs.
+// ------------------------------------------------------------------------------------------------
+template <bool kImage>
+__global__ void __launch_bounds__(256, 4)
+thin_persistent_kernel(const __grid_constant__ CameraState cam, const float4* __restrict__ samples, uint64_t n,
+                       uint64_t first_index, uint64_t seed, float4* __restrict__ origin_w, float4* __restrict__ dir_tries,
+                       DeviceStats* stats, int stage_rows, unsigned long long* chunk_counter) {
+    extern __shared__ float smem[];
+    BokehView bk;
+    if (kImage) bk = stage_bokeh(cam, smem, stage_rows != 0);
+    const ThinState& T = cam.thin;
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    LocalStats ls = {0, 0, 0, 0, 0, 0, 0};
+    uint64_t cur = 0, end = 0;
+    bool exhausted = false, have = false, fresh = false;
+    uint64_t idx = 0;
+    Vec3 focus = vmake(0.0f, 0.0f, 0.0f);
+    Xor128 rng = {0, 0, 0, 0};
+    int tries = 0;
+    float ua = 0.0f, ub = 0.0f;
+
+    for (;;) {
+        const unsigned need = __ballot_sync(0xffffffffu, !have);
+        if (need) {
+            if (cur == end && !exhausted) {
+                unsigned long long base = 0;
+                if (lane == 0) base = atomicAdd(chunk_counter, (unsigned long long)kChunk);
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (base >= n) { exhausted = true; }
+                else { cur = base; end = (base + kChunk < n) ? base + kChunk : n; }
+            }
+            const unsigned avail = (unsigned)(end - cur);
+            const unsigned want = __popc(need);
+            const unsigned take = want < avail ? want : avail;
+            const unsigned rank = __popc(need & lt_mask);
+            if (!have && rank < take) {
+                idx = cur + rank;
+                const float4 s = __ldcs(samples + idx);
+                const Vec3 dir0 = vnormalize(vmake(xmul(s.x, T.tan_fov), xmul(s.y, T.tan_fov), 1.0f));
+                focus = vscale(dir0, fabsf(xdiv(T.focal_distance, dir0.z)));
+                ua = s.z;
+                ub = s.w;
+                tries = 0;
+                have = true;
+                fresh = true;
+            }
+            cur += take;
+        }
+        if (!__any_sync(0xffffffffu, have)) {
+            if (exhausted) break;
+            continue;
+        }
+        if (have && !fresh) {
+            if (tries == 0) rng = sample_stream(seed, first_index + idx);
+            draw_pair(rng, &ua, &ub);
+            ++tries;
+        }
+        fresh = false;
+        float lx, ly;
+        lens_sample<kImage>(bk, ua, ub, &lx, &ly);
+        const Vec3 origin = vmake(xmul(lx, T.aperture_radius), xmul(ly, T.aperture_radius), 0.0f);
+        const Vec3 dir = vnormalize(vsub(focus, origin));
+        const float qx = xsub(xmul(dir.x, T.ov_distance), origin.x);
+        const float qy = xsub(xmul(dir.y, T.ov_distance), origin.y);
+        const float hyp = xsqrt(xadd(xmul(qx, qx), xmul(qy, qy)));
+        const bool pass = fabsf(hyp) < T.ov_radius_true;
+        if (have) {
+            ls.attempts++;
+            // the reference stops sampling once tries has passed maxtries, whatever the last test said
+            if (pass || tries > kMaxTries) {
+                float weight = 1.0f;
+                if (tries > kMaxTries) { weight = 0.0f; ls.vignetted++; }
+                else ls.success++;
+                weight = xmul(weight, cam.weight_scale);
+                __stcs(origin_w + idx, make_float4(origin.x, origin.y, origin.z, weight));
+                __stcs(dir_tries + idx, make_float4(dir.x, dir.y, -dir.z, (float)tries));
+                ls.rays++;
+                have = false;
+            }
+        }
+    }
+    flush_stats(ls, stats);
+}
+
+// ------------------------------------------------------------------------------------------------
 // synthetic samples
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
@@ -635,6 +723,14 @@ static cudaError_t launch_variant(const CameraState& cam, int mode, const float4
         rerun_kernel<kModel, kImage, kLut><<<(unsigned)sm_count() * 2, threads, smem, st>>>(
             cam, samples, first_index, seed, origin_w, dir_tries, stats, stage, ws.queue, ws.counters + 1, ws.capacity);
         if (launches) *launches += 2;
+        return cudaGetLastError();
+    }
+    if (mode == 1 && kModel == 0 && cam.thin.use_dof && cam.thin.use_ov) {  // retry loop present: persistent schedule
+        cudaError_t e = cudaMemsetAsync(ws.counters, 0, 2 * sizeof(unsigned long long), st);
+        if (e != cudaSuccess) return e;
+        thin_persistent_kernel<kImage><<<(unsigned)sm_count() * 4, threads, smem, st>>>(cam, samples, n, first_index, seed, origin_w,
+                                                                                      dir_tries, stats, stage, ws.counters);
+        if (launches) *launches += 1;
         return cudaGetLastError();
     }
     exact_kernel<kModel, kImage, kLut><<<grid_for(n, threads, 8), threads, smem, st>>>(cam, samples, n, first_index, seed,
