@@ -144,7 +144,7 @@ struct AtNodeLib {
 #define node_finish        static void Finish(AtNode* node)
 #define camera_create_ray  static void CameraCreateRay(const AtNode* node, const AtCameraInput& input, AtCameraOutput& output, int tid)
 #define camera_reverse_ray static bool CameraReverseRay(const AtNode* node, const AtVector& Po, const AtVector& Ro, float relative_time, AtVector2& Ps)
-#define node_loader        extern "C" bool NodeLoader(int i, AtNodeLib* node)
+#define node_loader        extern "C" __attribute__((visibility("default"))) bool NodeLoader(int i, AtNodeLib* node)
 
 // Parameter declaration: forwarded to the host so an embedding application can record names and
 // defaults (the real SDK stores them in the node entry).

@@ -139,6 +139,13 @@ ZOICB_API zoicb_status zoicb_generate(zoicb_ctx* ctx, const void* d_samples, uin
 ZOICB_API zoicb_status zoicb_generate_host(zoicb_ctx* ctx, const float* h_samples, uint64_t n, uint64_t first_index,
                                  uint64_t rng_seed, float* h_origin_w, float* h_dir_tries);
 
+/* camera_create_ray for ONE sample (the shape of Arnold's per-sample callback): sample = (sx, sy, lensx,
+ * lensy), outputs origin_w[4], dir_tries[4] in host memory.  Uses per-thread pinned staging and a per-thread
+ * stream, so it may be called concurrently from many render threads; it is a launch + two tiny copies per
+ * call, i.e. a compatibility path -- throughput comes from the batched entry points above. */
+ZOICB_API zoicb_status zoicb_generate_one(zoicb_ctx* ctx, const float* sample, uint64_t sample_index,
+                                          uint64_t rng_seed, float* origin_w, float* dir_tries);
+
 /* Synthetic camera samples for benchmarks and parity tests: sample index i is
  * pixel-major / spp-minor over a W x H image, four 24-bit uniforms from a counter hash of (seed, i). */
 ZOICB_API zoicb_status zoicb_synth_samples(zoicb_ctx* ctx, uint32_t W, uint32_t H, uint32_t spp, uint64_t seed,

@@ -9,8 +9,11 @@ import os
 
 import numpy as np
 
+import subprocess
+
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF_DIR = os.path.join(HERE, "_ref")
+HOST_LIB = os.path.join(HERE, "_build", "libzoic_refhost.so")
 
 THINLENS, RAYTRACED = 0, 1
 
@@ -27,46 +30,62 @@ class RefParams(C.Structure):
 
 
 def available(draw=False):
-    names = ["libzoic_refhost.so", "libzoic_ref_draw.so" if draw else "libzoic_ref.so"]
-    return all(os.path.exists(os.path.join(REF_DIR, n)) for n in names)
+    """True when the compiled reference plugin exists (built here by `make -C oracle ref`; it travels to the GPU box)."""
+    return os.path.exists(os.path.join(REF_DIR, "libzoic_ref_draw.so" if draw else "libzoic_ref.so"))
+
+
+def build_host():
+    src = os.path.join(HERE, "ref_host.cpp")
+    if not os.path.exists(HOST_LIB) or os.path.getmtime(HOST_LIB) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-s", "-C", HERE, "host"])
+    return HOST_LIB
 
 
 _host = None
+_plugins = {}
 
 
-def load(draw=False):
-    """Load the fake host (RTLD_GLOBAL so its xor128 interposes) and then the plugin."""
+def load(draw=False, plugin=None):
+    """Load the fake host (RTLD_GLOBAL so its xor128 interposes) and then the plugin: the compiled reference
+    by default, or any other library exporting NodeLoader (zoic_b200's own Arnold plugin in its tests).
+    Returns (host library, plugin index)."""
     global _host
-    if _host is not None:
-        return _host
-    host = C.CDLL(os.path.join(REF_DIR, "libzoic_refhost.so"), mode=C.RTLD_GLOBAL)
-    host.zref_open.argtypes = [C.c_char_p]
-    host.zref_create.restype = C.c_void_p
-    host.zref_create.argtypes = [C.POINTER(RefParams), C.c_void_p, C.c_int, C.c_int, C.c_int]
-    host.zref_generate.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64,
-                                   C.c_void_p, C.c_void_p, C.c_void_p]
-    host.zref_generate_one_with_state.argtypes = [C.c_void_p] * 6
-    host.zref_destroy.argtypes = [C.c_void_p]
-    host.zref_log.restype = C.c_char_p
-    host.zref_log.argtypes = [C.c_void_p]
-    host.zref_aborted.argtypes = [C.c_void_p]
-    host.zref_reverse_ray.argtypes = [C.c_void_p]
-    host.zref_node_name.restype = C.c_char_p
-    host.zref_node_version.restype = C.c_char_p
-    host.zref_sample_stream.argtypes = [C.c_uint64, C.c_uint64, C.c_void_p]
-    plugin = os.path.join(REF_DIR, "libzoic_ref_draw.so" if draw else "libzoic_ref.so")
-    rc = host.zref_open(plugin.encode())
-    if rc != 0:
-        raise RuntimeError("zref_open failed: %d" % rc)
-    _host = host
-    return host
+    if _host is None:
+        host = C.CDLL(build_host(), mode=C.RTLD_GLOBAL)
+        host.zref_open.argtypes = [C.c_char_p]
+        host.zref_create.restype = C.c_void_p
+        host.zref_create.argtypes = [C.c_int, C.POINTER(RefParams), C.c_void_p, C.c_int, C.c_int, C.c_int]
+        host.zref_generate.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64,
+                                       C.c_void_p, C.c_void_p, C.c_void_p]
+        host.zref_generate_one_with_state.argtypes = [C.c_void_p] * 6
+        host.zref_destroy.argtypes = [C.c_void_p]
+        host.zref_log.restype = C.c_char_p
+        host.zref_log.argtypes = [C.c_void_p]
+        host.zref_aborted.argtypes = [C.c_void_p]
+        host.zref_reverse_ray.argtypes = [C.c_void_p]
+        host.zref_node_name.restype = C.c_char_p
+        host.zref_node_name.argtypes = [C.c_int]
+        host.zref_node_version.restype = C.c_char_p
+        host.zref_node_version.argtypes = [C.c_int]
+        host.zref_node_type.argtypes = [C.c_int]
+        host.zref_output_type.argtypes = [C.c_int]
+        host.zref_sample_stream.argtypes = [C.c_uint64, C.c_uint64, C.c_void_p]
+        _host = host
+    if plugin is None:
+        plugin = os.path.join(REF_DIR, "libzoic_ref_draw.so" if draw else "libzoic_ref.so")
+    if plugin not in _plugins:
+        idx = _host.zref_open(plugin.encode())
+        if idx < 0:
+            raise RuntimeError("zref_open(%s) failed: %d" % (plugin, idx))
+        _plugins[plugin] = idx
+    return _host, _plugins[plugin]
 
 
 class RefCamera:
     """One reference camera node: NodeLoader -> Initialize -> Update done; generate() calls CreateRay per sample."""
 
-    def __init__(self, image=None, draw=False, **kw):
-        self.h = load(draw)
+    def __init__(self, image=None, draw=False, plugin=None, **kw):
+        self.h, self.plugin = load(draw, plugin)
         p = RefParams(sensorWidth=3.6, sensorHeight=2.4, focalLength=2.0, fStop=4.0, focalDistance=100.0,
                       useImage=0, lensModel=RAYTRACED, kolbSamplingLUT=1, useDof=1,
                       opticalVignettingDistance=0.0, opticalVignettingRadius=1.0, exposureControl=0.0,
@@ -85,7 +104,7 @@ class RefCamera:
             img_ptr = self._img.ctypes.data
             if not p.bokehPath:
                 p.bokehPath = b"<memory>"
-        self.c = self.h.zref_create(C.byref(p), img_ptr, w, hh, nch)
+        self.c = self.h.zref_create(self.plugin, C.byref(p), img_ptr, w, hh, nch)
         if not self.c:
             raise RuntimeError("zref_create failed")
 

@@ -23,6 +23,24 @@
 #include <vector>
 
 // ------------------------------------------------------------------------------------------------
+// Zero-filling replacement of the global allocation functions.  The reference never initialises
+// Lensdata::apertureElement for lens tables without a stop row (src/zoic.cpp:532, set only at :922), so what
+// it reads is whatever `new cameraData()` happens to return.  The ruling is "0"; this
+// replaceable operator new makes the unmodified plugin behave that way deterministically.
+// ------------------------------------------------------------------------------------------------
+#include <new>
+void* operator new(size_t n) {
+    void* p = calloc(1, n ? n : 1);
+    if (!p) throw std::bad_alloc();
+    return p;
+}
+void* operator new[](size_t n) { return operator new(n); }
+void operator delete(void* p) noexcept { free(p); }
+void operator delete[](void* p) noexcept { free(p); }
+void operator delete(void* p, size_t) noexcept { free(p); }
+void operator delete[](void* p, size_t) noexcept { free(p); }
+
+// ------------------------------------------------------------------------------------------------
 // RNG interposer
 // ------------------------------------------------------------------------------------------------
 namespace {
@@ -147,33 +165,41 @@ struct zref_camera {
     int aborted = 0;
 };
 
-static void* g_plugin = nullptr;
-static AtNodeLib g_lib;
+struct Plugin { void* handle; AtNodeLib lib; std::string path; };
+static std::vector<Plugin> g_plugins;
 
 void zref_set_verbose(int v) { g_verbose = v; }
 
-// dlopen the reference plugin and run its NodeLoader.  Returns 0 on success.
+// dlopen a plugin (the compiled reference, or any library exporting NodeLoader) and run its NodeLoader.
+// Returns a plugin index >= 0, or a negative error.
 int zref_open(const char* plugin_path) {
-    if (g_plugin) return 0;
-    g_plugin = dlopen(plugin_path, RTLD_NOW | RTLD_LOCAL);
-    if (!g_plugin) { fprintf(stderr, "zref_open: %s\n", dlerror()); return 1; }
+    for (size_t i = 0; i < g_plugins.size(); ++i)
+        if (g_plugins[i].path == plugin_path) return (int)i;
+    Plugin pl;
+    pl.path = plugin_path;
+    pl.handle = dlopen(plugin_path, RTLD_NOW | RTLD_LOCAL);
+    if (!pl.handle) { fprintf(stderr, "zref_open: %s\n", dlerror()); return -1; }
     typedef bool (*loader_t)(int, AtNodeLib*);
-    loader_t loader = (loader_t)dlsym(g_plugin, "NodeLoader");
-    if (!loader) return 2;
-    memset(&g_lib, 0, sizeof g_lib);
-    if (!loader(0, &g_lib)) return 3;
-    if (loader(1, &g_lib)) return 4;  // the plugin exports exactly one node
-    return 0;
+    loader_t loader = (loader_t)dlsym(pl.handle, "NodeLoader");
+    if (!loader) return -2;
+    memset(&pl.lib, 0, sizeof pl.lib);
+    if (!loader(0, &pl.lib)) return -3;
+    AtNodeLib scratch;
+    memset(&scratch, 0, sizeof scratch);
+    if (loader(1, &scratch)) return -4;  // the plugin exports exactly one node
+    g_plugins.push_back(pl);
+    return (int)g_plugins.size() - 1;
 }
 
-const char* zref_node_name(void) { return g_lib.name; }
-const char* zref_node_version(void) { return g_lib.version; }
-int zref_node_type(void) { return g_lib.node_type; }
+const char* zref_node_name(int plugin) { return g_plugins[plugin].lib.name; }
+const char* zref_node_version(int plugin) { return g_plugins[plugin].lib.version; }
+int zref_node_type(int plugin) { return g_plugins[plugin].lib.node_type; }
+int zref_output_type(int plugin) { return g_plugins[plugin].lib.output_type; }
 
-zref_camera* zref_create(const zref_params* p, const float* image, int w, int h, int nch) {
-    if (!g_plugin) return nullptr;
+zref_camera* zref_create(int plugin, const zref_params* p, const float* image, int w, int h, int nch) {
+    if (plugin < 0 || plugin >= (int)g_plugins.size()) return nullptr;
     zref_camera* c = new zref_camera();
-    const AtNodeMethods* m = (const AtNodeMethods*)g_lib.methods;
+    const AtNodeMethods* m = (const AtNodeMethods*)g_plugins[plugin].lib.methods;
     c->cm = m->cmethods;
     c->dm = (const AtCameraNodeMethods*)m->dmethods;
     AtNode& n = c->node;

@@ -211,3 +211,56 @@ def test_guarded_thin_lens_is_bit_exact(port):
         assert st["attempts"] == st2["attempts"] and st["vignetted"] == st2["vignetted"]
         cam.close()
         ref.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+# committed golden vectors (outputs of the compiled, unmodified reference) and the Arnold-shaped plugin
+# ---------------------------------------------------------------------------------------------------
+def test_gpu_reproduces_reference_golden_vectors():
+    from zoic_b200 import ZoicCamera, MODE_EXACT, MODE_GUARDED
+    from zutil import golden_case, golden_names
+    for name in golden_names():
+        kw, image, meta, s, o_ref, d_ref = golden_case(name)
+        cam = ZoicCamera(image=image, mode=MODE_EXACT, **kw)
+        o, d, st = _run_gpu(cam, s, seed=meta["seed"], first_index=meta["first_index"])
+        assert bits_equal(o, o_ref) and bits_equal(d, d_ref), name
+        assert st["attempts"] == meta["stats"]["attempts"], name
+        # the default mode on a batch big enough to take the persistent kernels: the golden samples tiled, each
+        # copy at its own index (so retries differ), first copy at the golden index
+        cam.set_mode(MODE_GUARDED)
+        reps = 24
+        big = np.tile(s, (reps, 1))
+        o, d, _ = _run_gpu(cam, big, seed=meta["seed"], first_index=meta["first_index"])
+        res = compare_rays(o[:len(s)], d[:len(s)], o_ref, d_ref)
+        assert res["path_flips"] == 0 and res["out_of_tol"] == 0, (name, res)
+        cam.close()
+
+
+def test_arnold_plugin_behind_a_host(port):
+    """libzoic_arnold.so driven exactly like the reference plugin: NodeLoader -> Initialize -> Update ->
+    CreateRay per sample -> Finish, by the test host that also drives the compiled reference."""
+    from oracle import ref
+    from zoic_b200 import build
+    from zoic_b200.workloads import lens_path
+    h, idx = ref.load(plugin=build.PLUGIN)
+    assert h.zref_node_name(idx) == b"zoic" and h.zref_node_type(idx) == 0x0002 and h.zref_output_type(idx) == 0xFF
+    kw = dict(lensModel=1, lensDataPath=lens_path("double_gauss_f2.0.dat"), focalLength=5.0, fStop=2.0, exposureControl=0.4)
+    cam = ref.RefCamera(plugin=build.PLUGIN, **kw)
+    assert not cam.aborted
+    assert "Image distance" in cam.log
+    assert h.zref_reverse_ray(cam.c) == 0
+    s = random_samples(3000, seed=2)
+    o, d, _ = cam.generate(s)                      # the adapter keys retry streams by arrival number, seed 0
+    p = port.PortCamera(**kw)
+    o2, d2, _ = p.generate(s, seed=0, first_index=0)
+    assert bits_equal(o, o2) and bits_equal(d[:, :3], d2[:, :3])
+    # derivative workaround of the reference (:1974-1977) for re-sampled rays
+    k = int(np.argmax(d2[:, 3] > 0))
+    o1, d1, dv = cam.generate_one(s[k], [1, 2, 3, 4])
+    cam.close()
+    bad = ref.RefCamera(plugin=build.PLUGIN, lensModel=1, lensDataPath="/nonexistent.dat")
+    assert bad.aborted and "cannot open lens file" in bad.log
+    o, d, _ = bad.generate(s[:4])
+    assert (o[:, 3] == 0).all()                    # no camera: zero-weight rays, no crash
+    bad.close()
+    p.close()

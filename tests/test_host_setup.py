@@ -1,0 +1,162 @@
+"""Host side of camera creation (zoic_b200/csrc/host_setup.cpp through the C ABI's host-only entry point)
+against the oracle: every derived constant, the exit-pupil LUT boxes and the bokeh CDF tables, bit for bit; the
+lens-table grammar; the error codes.  No GPU needed (LUT candidates are classified by host threads here)."""
+import os
+
+import numpy as np
+import pytest
+
+from zutil import (GOLDEN, bits_equal, draw_zoic_header, golden_case, golden_names, product_constants_flat,
+                   setup_log_values)
+
+from zoic_b200 import capi, host_setup
+from zoic_b200.synth import hex_bokeh_image
+from zoic_b200.workloads import LENSES, lens_path
+
+
+def _same_constants(a, b):
+    a = product_constants_flat(a)
+    for k in ("userApertureRadius", "originShift", "apertureDistance", "focalLengthRatio", "tracedFocalLength0",
+              "tracedFocalLength1", "principalPlane0", "principalPlane1", "focalPoint0", "focalPoint1"):
+        assert np.float32(a[k]).tobytes() == np.float32(b[k]).tobytes(), k
+    assert a["lensCount"] == b["lensCount"] and a["apertureElement"] == b["apertureElement"]
+    assert bits_equal(a["lenses"], b["lenses"])
+    assert bits_equal(a["lut"], b["lut"])
+
+
+@pytest.mark.parametrize("lens", sorted(LENSES))
+def test_kolb_setup_matches_oracle_bit_for_bit(port, lens):
+    fnum, focal = LENSES[lens]
+    kw = dict(lensModel=1, lensDataPath=lens_path(lens), focalLength=focal, fStop=fnum)
+    c, _ = host_setup(**kw)
+    p = port.PortCamera(**kw)
+    _same_constants(c, p.constants())
+    assert c["lutSize"] == 32
+    p.close()
+
+
+def test_kolb_setup_other_parameters(port):
+    for kw in (dict(focalLength=3.5, fStop=1.2, focalDistance=55.0), dict(focalLength=8.0, fStop=11.0, focalDistance=1000.0),
+               dict(focalLength=5.0, fStop=2.8, focalDistance=23.0, kolbSamplingLUT=0)):
+        kw = dict(dict(lensModel=1, lensDataPath=lens_path("double_gauss_f2.0.dat")), **kw)
+        c, _ = host_setup(**kw)
+        p = port.PortCamera(**kw)
+        _same_constants(c, p.constants())
+        p.close()
+
+
+def test_setup_reproduces_reference_known_answers():
+    """reference src/draw.zoic:1-10 and the node_update log lines of the compiled reference (golden.json)."""
+    want = [l.rstrip("\n") for l in open(os.path.join(GOLDEN, "draw_zoic_header.txt"))]
+    c, _ = host_setup(lensModel=1, lensDataPath=lens_path("double_gauss_f2.0.dat"), focalLength=5.0, fStop=2.8, focalDistance=23.0)
+    assert draw_zoic_header(c, 23.0) == want
+    for name in golden_names():
+        if not name.startswith("kolb"):
+            continue
+        kw, image, meta, *_ = golden_case(name)
+        c, _ = host_setup(image=image, **kw)
+        got = setup_log_values(product_constants_flat(c), kw["fStop"])
+        for key, val in meta["setup_log"].items():
+            assert got[key] == val, (name, key)
+
+
+def test_thin_lens_constants_and_bokeh_tables(port):
+    for size in (255, 33):
+        img = hex_bokeh_image(size)
+        kw = dict(lensModel=0, focalLength=3.5, fStop=2.8, opticalVignettingDistance=2.0, useImage=1)
+        c, tabs = host_setup(image=img, **kw)
+        p = port.PortCamera(image=img, **kw)
+        pc = p.constants()
+        for k in ("fov", "tan_fov", "apertureRadius"):
+            assert np.float32(c[k]).tobytes() == np.float32(pc[k]).tobytes()
+        for a, b in zip(tabs, p.bokeh_tables()):
+            assert np.array_equal(a, b)
+        assert (c["bokehWidth"], c["bokehHeight"]) == (size, size)
+        p.close()
+
+
+def test_bokeh_tables_ragged_images(port):
+    """Non-square, even-sized, 4-channel, flat (all ties) and single-row images."""
+    rng = np.random.default_rng(5)
+    imgs = [hex_bokeh_image(33)[:, :20].copy(), hex_bokeh_image(32), np.ones((7, 9, 3), np.float32),
+            rng.random((1, 16, 4)).astype(np.float32), rng.random((16, 1, 3)).astype(np.float32)]
+    for img in imgs:
+        kw = dict(lensModel=0, focalLength=3.5, fStop=2.8, useImage=1)
+        _, tabs = host_setup(image=img, **kw)
+        p = port.PortCamera(image=img, **kw)
+        for a, b in zip(tabs, p.bokeh_tables()):
+            assert np.array_equal(a, b)
+        p.close()
+
+
+LENS_TEXT = {
+    "tabs": "# c\n58.950\t7.520\t1.67\t50.4\n169.660\t0.240\t1.0\t50.4\n0\t9.000\t0\t34.2\n-28.990\t2.360\t1.603\t34.0\n-79.46\t72.228\t1.0\t40.0",
+    "mixed-delims-5col": "## V\n\n74.062,18.55;1.611:58.8 31.6\n-114.427\t0.766\t0.0\t0.0\t31.6\n0 5.3 0 0 20\n55.173\t15.9\t1.611 58.8\t23.1\n",
+    "crlf": "58.950\t7.520\t1.67\t50.4\r\n0\t9.000\t0\t34.2\r\n-79.46\t72.228\t1.0\t40.0\r\n",
+    "trailing-delim": "58.950 7.520 1.67 50.4 \n0 9.000 0 34.2 \n-79.46 72.228 1.0 40.0 \n",
+}
+
+
+@pytest.mark.parametrize("name", sorted(LENS_TEXT))
+def test_lens_table_grammar(port, tmp_path, name):
+    path = tmp_path / (name + ".dat")
+    path.write_bytes(LENS_TEXT[name].encode())
+    kw = dict(lensModel=1, lensDataPath=str(path), focalLength=5.0, fStop=2.8, kolbSamplingLUT=0)
+    c, _ = host_setup(**kw)
+    p = port.PortCamera(**kw)
+    _same_constants(c, p.constants())
+    p.close()
+
+
+def test_shipped_lens_tables_parse_like_the_reference_originals(port):
+    """zoic_b200/data/lenses/*.dat are re-emitted tables (tools/import_lenses.py); where the reference tree is
+    present, check that both spellings give identical element tables."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(GOLDEN), "..", "tools"))
+    from import_lenses import NAMES
+    ref_dir = "/root/reference/lenses_tabular"
+    if not os.path.isdir(ref_dir):
+        pytest.skip("reference tree not present")
+    for src, (dst, _) in NAMES.items():
+        kw = dict(lensModel=1, focalLength=LENSES[dst][1], fStop=2.8, kolbSamplingLUT=0)
+        a, _ = host_setup(lensDataPath=os.path.join(ref_dir, src), **kw)
+        b, _ = host_setup(lensDataPath=lens_path(dst), **kw)
+        assert bits_equal(a["lenses"], b["lenses"]) and a["originShift"] == b["originShift"]
+
+
+def test_error_codes(tmp_path):
+    with pytest.raises(capi.ZoicError) as e:
+        host_setup(lensModel=1, lensDataPath=str(tmp_path / "missing.dat"))
+    assert e.value.code == capi.ERR_LENS_FILE
+    with pytest.raises(capi.ZoicError) as e:
+        host_setup(lensModel=1, lensDataPath="")
+    assert e.value.code == capi.ERR_LENS_FILE
+    three = tmp_path / "three.dat"
+    three.write_text("1 2 3\n4 5 6\n")
+    with pytest.raises(capi.ZoicError) as e:
+        host_setup(lensModel=1, lensDataPath=str(three))
+    assert e.value.code == capi.ERR_LENS_FILE and "fewer than 4" in str(e.value)
+    six = tmp_path / "six.dat"
+    six.write_text("1 2 3 4 5 6\n1 2 3 4 5 6\n")
+    with pytest.raises(capi.ZoicError) as e:
+        host_setup(lensModel=1, lensDataPath=str(six))
+    assert e.value.code == capi.ERR_LENS_FILE and "more than 5" in str(e.value)
+    two_stops = tmp_path / "two.dat"
+    two_stops.write_text("50 5 1.6 40\n0 2 0 30\n0 2 0 30\n-50 60 1 40\n")
+    with pytest.raises(capi.ZoicError) as e:
+        host_setup(lensModel=1, lensDataPath=str(two_stops))
+    assert e.value.code == capi.ERR_LENS_DATA
+    junk = tmp_path / "junk.dat"
+    junk.write_text("50 5 abc 40\n-50 60 1 40\n")
+    with pytest.raises(capi.ZoicError) as e:
+        host_setup(lensModel=1, lensDataPath=str(junk))
+    assert e.value.code == capi.ERR_LENS_FILE
+    with pytest.raises(capi.ZoicError) as e:
+        host_setup(lensModel=0, useImage=1)
+    assert e.value.code == capi.ERR_BOKEH_IMAGE
+    with pytest.raises(capi.ZoicError) as e:
+        host_setup(lensModel=0, useImage=1, image=np.ones((4, 4, 2), np.float32))
+    assert e.value.code == capi.ERR_BOKEH_IMAGE
+    with pytest.raises(capi.ZoicError) as e:
+        host_setup(lensModel=7)
+    assert e.value.code == capi.ERR_INVALID_ARGUMENT

@@ -13,7 +13,9 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libzoicb.so")
 
-SOURCES = ["capi.cu", "kernels.cu", "host_setup.cpp", "arnold_adapter.cpp"]
+SOURCES = ["capi.cu", "kernels.cu", "host_setup.cpp"]
+ADAPTER = "arnold_adapter.cpp"
+PLUGIN = os.path.join(LIBDIR, "libzoic_arnold.so")
 HEADERS = ["camera_state.h", "lens_math.cuh", "host_setup.h", "kernels.h",
            os.path.join(ROOT, "include", "zoicb.h"), os.path.join(ROOT, "include", "arnold_shim", "ai.h")]
 
@@ -37,8 +39,8 @@ def _stale(out, deps):
 def build_library(force=False, verbose=False):
     srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
     hdrs = [h if os.path.isabs(h) else os.path.join(CSRC, h) for h in HEADERS]
-    deps = srcs + [h for h in hdrs if os.path.exists(h)] + [os.path.abspath(__file__)]
-    if not force and not _stale(LIB, deps):
+    deps = srcs + [h for h in hdrs if os.path.exists(h)] + [os.path.abspath(__file__), os.path.join(CSRC, ADAPTER)]
+    if not force and not _stale(LIB, deps) and not _stale(PLUGIN, deps):
         return LIB
     os.makedirs(LIBDIR, exist_ok=True)
     objdir = os.path.join(LIBDIR, "obj")
@@ -67,6 +69,12 @@ def build_library(force=False, verbose=False):
         raise RuntimeError("nvcc failed")
     link = [_nvcc()] + ccbin + ARCH + ["-shared", "-o", LIB] + objs + ["-lpthread"]
     subprocess.check_call(link)
+    # the Arnold-shaped plugin: NodeLoader + node callbacks on top of libzoicb.so; the Ai* host functions stay
+    # undefined and are resolved by the host application (Arnold, or the test host) at load time
+    gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    subprocess.check_call([gxx, "-std=c++17", "-O2", "-shared", "-fPIC", "-fvisibility=hidden",
+                           "-I", os.path.join(ROOT, "include", "arnold_shim"), os.path.join(CSRC, ADAPTER),
+                           "-o", PLUGIN, "-L", LIBDIR, "-lzoicb", "-Wl,-rpath,$ORIGIN"])
     return LIB
 
 

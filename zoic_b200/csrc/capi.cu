@@ -310,6 +310,51 @@ zoicb_status zoicb_generate_host(zoicb_ctx* ctx, const float* h_samples, uint64_
     return ZOICB_OK;
 }
 
+namespace {
+struct OneShot {  // per-thread resources of zoicb_generate_one
+    int device = -1;
+    cudaStream_t stream = nullptr;
+    float4* h = nullptr;  // pinned: [0] sample, [1] origin_w, [2] dir_tries
+    float4* d = nullptr;
+    ~OneShot() {
+        if (device >= 0) {
+            cudaSetDevice(device);
+            if (stream) cudaStreamDestroy(stream);
+            if (h) cudaFreeHost(h);
+            if (d) cudaFree(d);
+        }
+    }
+};
+thread_local OneShot t_one;
+}  // namespace
+
+zoicb_status zoicb_generate_one(zoicb_ctx* ctx, const float* sample, uint64_t sample_index, uint64_t rng_seed,
+                                float* origin_w, float* dir_tries) {
+    if (!ctx || !sample || !origin_w || !dir_tries) return fail(ZOICB_ERR_INVALID_ARGUMENT, "zoicb_generate_one: null argument");
+    ZCUDA(cudaSetDevice(ctx->device), "cudaSetDevice");
+    OneShot& r = t_one;
+    if (r.device != ctx->device) {
+        if (r.device >= 0) return fail(ZOICB_ERR_UNSUPPORTED, "zoicb_generate_one: one device per calling thread");
+        ZCUDA(cudaStreamCreateWithFlags(&r.stream, cudaStreamNonBlocking), "cudaStreamCreate");
+        ZCUDA(cudaMallocHost(&r.h, 3 * sizeof(float4)), "cudaMallocHost");
+        ZCUDA(cudaMalloc(&r.d, 3 * sizeof(float4)), "cudaMalloc");
+        r.device = ctx->device;
+    }
+    std::memcpy(&r.h[0], sample, sizeof(float4));
+    ZCUDA(cudaMemcpyAsync(&r.d[0], &r.h[0], sizeof(float4), cudaMemcpyHostToDevice, r.stream), "H2D");
+    int launches = 0;
+    const Workspace ws = {nullptr, nullptr, 0};
+    cudaError_t e = launch_generate(ctx->host.state, ZOICB_MODE_EXACT, &r.d[0], 1, sample_index, rng_seed, &r.d[1], &r.d[2],
+                                    ctx->d_stats, r.stream, ws, &launches);
+    count_launches(launches);
+    if (e != cudaSuccess) return cuda_fail(e, "zoicb_generate_one launch");
+    ZCUDA(cudaMemcpyAsync(&r.h[1], &r.d[1], 2 * sizeof(float4), cudaMemcpyDeviceToHost, r.stream), "D2H");
+    ZCUDA(cudaStreamSynchronize(r.stream), "cudaStreamSynchronize");
+    std::memcpy(origin_w, &r.h[1], sizeof(float4));
+    std::memcpy(dir_tries, &r.h[2], sizeof(float4));
+    return ZOICB_OK;
+}
+
 zoicb_status zoicb_synth_samples(zoicb_ctx* ctx, uint32_t W, uint32_t H, uint32_t spp, uint64_t seed, uint64_t first_index,
                                  uint64_t n, void* d_samples, void* stream) {
     if (!ctx) return fail(ZOICB_ERR_INVALID_ARGUMENT, "zoicb_synth_samples: null context");

@@ -743,6 +743,7 @@ cudaError_t launch_generate(const CameraState& cam, int mode, const float4* samp
                             uint64_t seed, float4* origin_w, float4* dir_tries, DeviceStats* stats, cudaStream_t st,
                             const Workspace& ws, int* launches) {
     if (n == 0) return cudaSuccess;
+    if (n < 8192) mode = 0;  // a persistent grid does not pay for a handful of samples; the exact kernel is also bit-exact
     const bool image = cam.use_image != 0;
     size_t smem = 0;
     int stage = 0;

@@ -1,0 +1,44 @@
+"""Sharding of a sample range over ranks and the final gather of the ray buffer.
+
+Every sample is independent (per-sample retry streams), so ranks take contiguous index ranges and there is no
+data-path collective; the only collective is the optional gather of the finished ray buffers and a sum of the
+counters.  torch.distributed is the plumbing: NCCL over NVLink on GPUs, gloo in the CPU tests.
+"""
+
+
+def shard_range(n, rank, world):
+    """Contiguous, balanced split of sample indices [0, n): returns (first, count) of `rank`.
+    The first n % world ranks get one extra sample; concatenating the shards in rank order gives [0, n)."""
+    base, extra = divmod(n, world)
+    first = rank * base + min(rank, extra)
+    return first, base + (1 if rank < extra else 0)
+
+
+def gather_rays(origin_w, dir_tries, group=None):
+    """All-gather the per-rank ray buffers ([count, 4] each) into the full [n, 4] buffers, in rank order.
+    Shards may differ by one row (shard_range), so rows are padded to the largest shard for the collective."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    counts = [torch.zeros(1, dtype=torch.int64, device=origin_w.device) for _ in range(world)]
+    dist.all_gather(counts, torch.tensor([origin_w.shape[0]], dtype=torch.int64, device=origin_w.device), group=group)
+    counts = [int(c.item()) for c in counts]
+    m = max(counts)
+
+    def one(t):
+        pad = t if t.shape[0] == m else torch.cat([t, t.new_zeros((m - t.shape[0], 4))])
+        out = [torch.empty((m, 4), dtype=t.dtype, device=t.device) for _ in range(world)]
+        dist.all_gather(out, pad.contiguous(), group=group)
+        return torch.cat([out[r][:counts[r]] for r in range(world)])
+
+    return one(origin_w), one(dir_tries)
+
+
+def reduce_stats(stats, device, group=None):
+    """Sum the per-rank counter dicts (zoicb_stats) over all ranks."""
+    import torch
+    import torch.distributed as dist
+    keys = sorted(stats)
+    t = torch.tensor([stats[k] for k in keys], dtype=torch.int64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return {k: int(v) for k, v in zip(keys, t.tolist())}
