@@ -264,3 +264,18 @@ def test_arnold_plugin_behind_a_host(port):
     assert (o[:, 3] == 0).all()                    # no camera: zero-weight rays, no crash
     bad.close()
     p.close()
+
+
+@pytest.mark.parametrize("size", [7, 32, 33, 65, 100])
+def test_guarded_kolb_bokeh_image_sizes(port, size):
+    """Image sizes that are not 2^k - 1 give the table searches lane-dependent lengths (regression: the
+    searches run a warp-uniform number of rounds)."""
+    from zoic_b200.synth import hex_bokeh_image
+    from zoic_b200.workloads import lens_path
+    img = hex_bokeh_image(size)
+    if size == 100:
+        img = img[:, :77].copy()
+    _check_guarded(dict(lensModel=1, lensDataPath=lens_path("double_gauss_f2.0.dat"), focalLength=5.0, fStop=2.0,
+                        useImage=1), port, n=60_000, image=img)
+    _check_exact(dict(lensModel=0, focalLength=3.5, fStop=2.8, opticalVignettingDistance=2.0, useImage=1), port,
+                 n=60_000, image=img)

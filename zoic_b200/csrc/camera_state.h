@@ -10,6 +10,7 @@ namespace zoicb {
 
 constexpr int kMaxElements = 24;
 constexpr int kLutSize = 32;
+constexpr int kMaxBokehRows = 5120;  // row CDF + row indices are staged in 40 KB of shared memory
 constexpr int kMaxTries = 25;  // reference src/zoic.cpp:1767
 
 // One refracting surface, rear element (nearest the sensor) first.  Everything the march needs per

@@ -336,6 +336,7 @@ zoicb_status build_bokeh(const float* rgb, int w, int h, int nch, HostBokeh* out
         return ZOICB_ERR_BOKEH_IMAGE;
     }
     if (w > 65535) { *err = "bokeh image wider than 65535 pixels"; return ZOICB_ERR_UNSUPPORTED; }
+    if (h > kMaxBokehRows) { *err = "bokeh image has more rows than the kernels stage in shared memory (5120)"; return ZOICB_ERR_UNSUPPORTED; }
     const int np = w * h;
     std::vector<float> lum(np), pdf(np), row_mass(h), cond(np);
     float total = 0.0f;

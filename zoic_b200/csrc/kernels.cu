@@ -17,37 +17,46 @@ namespace zoicb {
 // ------------------------------------------------------------------------------------------------
 // image-based aperture sampling (reference imageData::bokehSample, src/zoic.cpp:420-485)
 // ------------------------------------------------------------------------------------------------
-// std::upper_bound's probe sequence: first index whose value is greater than u
-__device__ __forceinline__ int upper_bound_idx(const float* __restrict__ a, int len, float u) {
-    int first = 0;
-    while (len > 0) {
-        int half = len >> 1;
-        int mid = first + half;
-        if (u < a[mid]) {
-            len = half;
-        } else {
-            first = mid + 1;
-            len = len - half - 1;
-        }
+// std::upper_bound over a[0..n): first index whose value is greater than u, with libstdc++'s probe sequence
+// (first/len halving).  The loop runs a warp-uniform number of rounds (bit length of n) with predicated
+// updates instead of a per-lane trip count: no divergence, and -- the reason it is written this way -- no
+// lane leaves the loop early.  (With a data-dependent trip count ptxas 12.9 let the early lanes run ahead and
+// re-use the uniform registers that hold the table pointers while the late lanes were still reading them.)
+template <typename Load>
+__device__ __forceinline__ int upper_bound_rounds(int n, float u, Load load) {
+    int first = 0, len = n;
+    const int rounds = 32 - __clz(n);  // len halves every round: n -> 0 in at most bit_length(n) rounds
+    for (int it = 0; it < rounds; ++it) {
+        const int half = len >> 1;
+        const int mid = first + half;
+        const float v = load(mid < n ? mid : n - 1);
+        const bool live = len > 0;
+        const bool left = u < v;
+        first = (live && !left) ? mid + 1 : first;
+        len = live ? (left ? half : len - half - 1) : 0;
     }
     return first;
 }
 
+// The row tables (cdfRow, rowIndices: 8 bytes per image row) are always staged in dynamic shared memory --
+// s_rows[0..h) holds the CDF, s_rows[h..2h) the row indices -- and addressed as shared memory (no generic
+// pointers); the per-row column tables stay in global memory (L1/L2 resident).
+extern __shared__ float s_rows[];
+
 struct BokehView {
-    const float* cdf_row;     // shared memory when staged, else global
-    const int32_t* row_idx;
-    const float* cdf_col;     // global (L1/L2 resident)
+    const float* cdf_col;     // global
     const uint16_t* rel_col;
     int w, h;
 };
 
 __device__ __forceinline__ void bokeh_sample(const BokehView& b, float u_row, float u_col, float* dx, float* dy) {
-    int r = upper_bound_idx(b.cdf_row, b.h, u_row);
+    int r = upper_bound_rounds(b.h, u_row, [&](int i) { return s_rows[i]; });
     if (r >= b.h) r = b.h - 1;
-    const int row = b.row_idx[r];
+    const int row = __float_as_int(s_rows[b.h + r]);
     const int rrow = row - ((b.w - 1) / 2);  // centred with the WIDTH (:441)
     const int start = row * b.w;
-    int c = upper_bound_idx(b.cdf_col + start, b.w, u_col);
+    const float* __restrict__ col = b.cdf_col + start;
+    int c = upper_bound_rounds(b.w, u_col, [&](int i) { return __ldg(col + i); });
     if (c >= b.w) c = b.w - 1;
     const int rel = (int)__ldg(b.rel_col + start + c);
     const int rcol = rel - ((b.h - 1) / 2);  // centred with the HEIGHT (:466)
@@ -72,25 +81,16 @@ __device__ __forceinline__ void draw_pair(Xor128& rng, float* first_param, float
     *first_param = u32_to_unit(k2);
 }
 
-__device__ __forceinline__ BokehView stage_bokeh(const CameraState& cam, float* smem, bool staged) {
+__device__ __forceinline__ BokehView stage_bokeh(const CameraState& cam) {
     BokehView b;
     b.w = cam.bokeh.w; b.h = cam.bokeh.h;
     b.cdf_col = cam.bokeh.cdf_column;
     b.rel_col = cam.bokeh.rel_column;
-    if (staged) {
-        float* s_cdf = smem;
-        int32_t* s_idx = reinterpret_cast<int32_t*>(smem + b.h);
-        for (int i = threadIdx.x; i < b.h; i += blockDim.x) {
-            s_cdf[i] = cam.bokeh.cdf_row[i];
-            s_idx[i] = cam.bokeh.row_indices[i];
-        }
-        __syncthreads();
-        b.cdf_row = s_cdf;
-        b.row_idx = s_idx;
-    } else {
-        b.cdf_row = cam.bokeh.cdf_row;
-        b.row_idx = cam.bokeh.row_indices;
+    for (int i = threadIdx.x; i < b.h; i += blockDim.x) {
+        s_rows[i] = cam.bokeh.cdf_row[i];
+        s_rows[b.h + i] = __int_as_float(cam.bokeh.row_indices[i]);
     }
+    __syncthreads();
     return b;
 }
 
@@ -254,9 +254,9 @@ __global__ void __launch_bounds__(256)
 exact_kernel(const __grid_constant__ CameraState cam, const float4* __restrict__ samples, uint64_t n,
              uint64_t first_index, uint64_t seed, float4* __restrict__ origin_w, float4* __restrict__ dir_tries,
              DeviceStats* stats, int stage_rows) {
-    extern __shared__ float smem[];
     BokehView bk;
-    if (kImage) bk = stage_bokeh(cam, smem, stage_rows != 0);
+    if (kImage) bk = stage_bokeh(cam);
+    (void)stage_rows;
     LocalStats ls = {0, 0, 0, 0, 0, 0, 0};
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
@@ -277,9 +277,9 @@ rerun_kernel(const __grid_constant__ CameraState cam, const float4* __restrict__
              uint64_t seed, float4* __restrict__ origin_w, float4* __restrict__ dir_tries, DeviceStats* stats,
              int stage_rows, const unsigned long long* __restrict__ queue, const unsigned long long* __restrict__ count,
              unsigned long long capacity) {
-    extern __shared__ float smem[];
     BokehView bk;
-    if (kImage) bk = stage_bokeh(cam, smem, stage_rows != 0);
+    if (kImage) bk = stage_bokeh(cam);
+    (void)stage_rows;
     LocalStats ls = {0, 0, 0, 0, 0, 0, 0};
     unsigned long long m = *count;
     if (m > capacity) m = capacity;
@@ -416,9 +416,9 @@ kolb_guarded_kernel(const __grid_constant__ CameraState cam, const float4* __res
                     uint64_t first_index, uint64_t seed, float4* __restrict__ origin_w, float4* __restrict__ dir_tries,
                     DeviceStats* stats, int stage_rows, unsigned long long* chunk_counter, unsigned long long* queue,
                     unsigned long long* queue_count, unsigned long long capacity) {
-    extern __shared__ float smem[];
     BokehView bk;
-    if (kImage) bk = stage_bokeh(cam, smem, stage_rows != 0);
+    if (kImage) bk = stage_bokeh(cam);
+    (void)stage_rows;
     const LensState& L = cam.lens;
     const unsigned lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
@@ -535,9 +535,9 @@ __global__ void __launch_bounds__(256, 4)
 thin_persistent_kernel(const __grid_constant__ CameraState cam, const float4* __restrict__ samples, uint64_t n,
                        uint64_t first_index, uint64_t seed, float4* __restrict__ origin_w, float4* __restrict__ dir_tries,
                        DeviceStats* stats, int stage_rows, unsigned long long* chunk_counter) {
-    extern __shared__ float smem[];
     BokehView bk;
-    if (kImage) bk = stage_bokeh(cam, smem, stage_rows != 0);
+    if (kImage) bk = stage_bokeh(cam);
+    (void)stage_rows;
     const ThinState& T = cam.thin;
     const unsigned lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
@@ -747,9 +747,9 @@ cudaError_t launch_generate(const CameraState& cam, int mode, const float4* samp
     const bool image = cam.use_image != 0;
     size_t smem = 0;
     int stage = 0;
-    if (image) {
-        size_t need = (size_t)cam.bokeh.h * 8;
-        if (need <= 40 * 1024) { smem = need; stage = 1; }
+    if (image) {  // row tables staged in shared memory; zoicb_create rejects images with more than kMaxBokehRows rows
+        smem = (size_t)cam.bokeh.h * 8;
+        stage = 1;
     }
 #define ZL(M, I, U) launch_variant<M, I, U>(cam, mode, samples, n, first_index, seed, origin_w, dir_tries, stats, st, ws, smem, stage, launches)
     if (cam.lens_model == 0) return image ? ZL(0, true, false) : ZL(0, false, false);
