@@ -102,6 +102,7 @@ typedef struct zoicb_constants {
     float aperture[ZOICB_MAX_ELEMENTS], center[ZOICB_MAX_ELEMENTS];
     float lutKey[ZOICB_LUT_SIZE];
     float lutMinX[ZOICB_LUT_SIZE], lutMinY[ZOICB_LUT_SIZE], lutMaxX[ZOICB_LUT_SIZE], lutMaxY[ZOICB_LUT_SIZE];
+    int32_t guardedSplit;   /* surfaces [0, split) / [split, lensCount): the two stages of the guarded kernel */
 } zoicb_constants;
 
 typedef struct zoicb_ctx zoicb_ctx;

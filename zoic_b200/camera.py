@@ -38,7 +38,8 @@ def make_params(**kw):
 
 def _constants_to_dict(c):
     n, nl = c.lensCount, c.lutSize
-    out = {k: getattr(c, k) for k in ("lensCount", "apertureElement", "lutSize", "bokehWidth", "bokehHeight")}
+    out = {k: getattr(c, k) for k in ("lensCount", "apertureElement", "lutSize", "bokehWidth", "bokehHeight",
+                                      "guardedSplit")}
     for k in ("fov", "tan_fov", "apertureRadius", "userApertureRadius", "originShift", "apertureDistance",
               "focalLengthRatio"):
         out[k] = np.float32(getattr(c, k))

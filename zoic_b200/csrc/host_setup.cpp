@@ -320,6 +320,49 @@ void build_lut(LensState* L, zoicb_constants* C, LutTraceFn fn, void* user) {
     C->lutSize = n_film;
 }
 
+// ------------------------------------------------------------------ stage boundary of the guarded kernel
+// The guarded kernel marches the surfaces in two stages with a warp-level compaction in between, so that rays
+// stopped early (rear rim, stop) do not idle through the rest of the stack.  Where to cut depends on where
+// this camera's attempts die: trace a few thousand attempts on the host (exact arithmetic, samples spread over
+// the sensor), histogram the stopping surface and minimise a simple issue-slot model.
+int choose_split(const LensState& L, float sensor_w, float sensor_h) {
+    const int n = L.count;
+    if (n < 2) return 1;
+    std::vector<double> stop_at(n, 0.0);
+    double pass = 0.0, total = 0.0;
+    Xor128 rng = {0x9E3779B9u, 0x243F6A88u, 0xB7E15162u, 0x8AED2A6Bu};
+    const float aspect = sensor_w > 0.0f ? sensor_h / sensor_w : 1.0f;
+    for (int s = 0; s < 6000; ++s) {
+        const float sx = 2.0f * u32_to_unit(xor128_next(rng)) - 1.0f;
+        const float sy = (2.0f * u32_to_unit(xor128_next(rng)) - 1.0f) * aspect;
+        const KolbSampleState k = L.use_lut ? kolb_sample_setup<true, true>(L, sx, sy) : kolb_sample_setup<false, true>(L, sx, sy);
+        for (int a = 0; a < 4; ++a) {  // a few attempts per film point
+            float lx, ly;
+            concentric_disk(u32_to_unit(xor128_next(rng)), u32_to_unit(xor128_next(rng)), &lx, &ly);
+            Ray r;
+            r.o = vmake(k.fx, k.fy, L.origin_shift);
+            r.d = L.use_lut ? kolb_aim<true>(L, k, lx, ly, a > 0) : kolb_aim<false>(L, k, lx, ly, a > 0);
+            int visited = 0;
+            const int rc = exact_march(L, r, &visited);
+            total += 1.0;
+            if (rc == kPass) pass += 1.0; else stop_at[visited - 1] += 1.0;
+        }
+    }
+    if (pass < 1.0) pass = 1.0;
+    const double setup = 130.0, per_surface = 66.0;
+    int best = 1;
+    double best_cost = 1e300;
+    for (int k = 1; k < n; ++k) {
+        double dead_a = 0.0, dead_b = 0.0;
+        for (int i = 0; i < n; ++i) (i < k ? dead_a : dead_b) += stop_at[i];
+        const double survive_a = (total - dead_a) / total;
+        const double util_b = survive_a > 0.0 ? 1.0 - 0.5 * (dead_b / total) / survive_a : 1.0;
+        const double cost = (setup + k * per_surface) + survive_a * (n - k) * per_surface / util_b + 40.0;
+        if (cost < best_cost) { best_cost = cost; best = k; }
+    }
+    return best;
+}
+
 // ------------------------------------------------------------------ bokeh tables (src/zoic.cpp:222-417)
 // Luminance -> normalised PDF -> rows sorted by descending mass -> per-row columns sorted by descending
 // conditional probability -> running sums.  Sums are sequential fp32 and the sorts are std::sort with a
@@ -472,6 +515,8 @@ zoicb_status build_camera(const zoicb_params& p, const float* rgb, int w, int h,
         C.aperture[i] = rows[i].aperture; C.center[i] = rows[i].center;
     }
     if (p.kolbSamplingLUT) build_lut(&L, &C, lut_fn, lut_user);  // :1691-1692
+    L.split = choose_split(L, p.sensorWidth, p.sensorHeight);
+    C.guardedSplit = L.split;
     return ZOICB_OK;
 }
 

@@ -9,6 +9,8 @@
 #include <cuda_runtime.h>
 #include <math_constants.h>
 
+#include <cstdlib>
+
 #include "kernels.h"
 #include "lens_math.cuh"
 
@@ -167,49 +169,6 @@ __device__ __forceinline__ void thin_exact_sample(const CameraState& cam, const 
 // ------------------------------------------------------------------------------------------------
 // EXACT raytraced lens, one sample (src/zoic.cpp:1850-1964, :1099-1158)
 // ------------------------------------------------------------------------------------------------
-struct KolbSampleState {  // per-sample constants of the retry loop
-    float fx, fy;          // film point (z = origin_shift)
-    float max_scale, translation, sn, cs;
-};
-
-// exact per-sample set-up: film point, exit-pupil LUT lookup, rotation (src/zoic.cpp:1853-1855, :1891-1911).
-// kAccurateAtan: theta through the double-precision atan2 the reference calls (bit parity) or atan2f.
-template <bool kLut, bool kAccurateAtan>
-__device__ __forceinline__ KolbSampleState kolb_sample_setup(const LensState& L, float sx, float sy) {
-    KolbSampleState k;
-    k.fx = xmul(sx, L.half_sensor);
-    k.fy = xmul(sy, L.half_sensor);
-    k.max_scale = L.first_aperture;
-    k.translation = 0.0f;
-    k.sn = 0.0f;
-    k.cs = 1.0f;
-    if (kLut) {
-        const float dist = fabsf(xsqrt(xadd(xmul(k.fx, k.fx), xmul(k.fy, k.fy))));
-        lut_lookup(L, dist, &k.max_scale, &k.translation);
-        float theta;
-        if (kAccurateAtan) theta = __double2float_rn(atan2((double)k.fy, (double)k.fx));  // :1899
-        else theta = atan2f(k.fy, k.fx);
-        k.sn = fast_sin(theta);
-        k.cs = fast_cos(theta);
-    }
-    return k;
-}
-
-// direction from the film point to the (scaled, translated, rotated) lens sample.  `retry` selects the
-// reference's retry arithmetic, which adds the translation to BOTH components (:1933 vs :1914).
-template <bool kLut>
-__device__ __forceinline__ Vec3 kolb_aim(const LensState& L, const KolbSampleState& k, float lx, float ly, bool retry) {
-    if (kLut) {
-        float px = xadd(xmul(lx, k.max_scale), k.translation);
-        float py = xmul(ly, k.max_scale);
-        if (retry) py = xadd(py, k.translation);
-        float rx = xsub(xmul(px, k.cs), xmul(py, k.sn));
-        float ry = xadd(xmul(px, k.sn), xmul(py, k.cs));
-        return vmake(xsub(rx, k.fx), xsub(ry, k.fy), L.neg_first_thickness);
-    }
-    return vmake(xsub(xmul(lx, k.max_scale), k.fx), xsub(xmul(ly, k.max_scale), k.fy), L.neg_first_thickness);
-}
-
 template <bool kImage, bool kLut>
 __device__ __forceinline__ void kolb_exact_sample(const CameraState& cam, const BokehView& bk, float4 s, uint64_t gidx,
                                                   uint64_t seed, float4* o4, float4* d4, LocalStats& ls) {
@@ -526,6 +485,265 @@ kolb_guarded_kernel(const __grid_constant__ CameraState cam, const float4* __res
 }
 
 // ------------------------------------------------------------------------------------------------
+// GUARDED kernel, two-stage schedule
+//
+// Lanes are stateless workers; the samples in flight live in a per-warp pool of kPoolSlots slots in shared
+// memory.  Stage A = (draw lens point, aim, surfaces [0, split)), stage B = surfaces [split, N).  After each
+// stage the warp sorts the slots it just worked on into three stacks with ballot + popc prefix sums -- rays
+// that still need an attempt (A), rays that survived stage A (B), free slots (F) -- and the next pass takes
+// 32 slots from whichever stack is full enough, so both stages run with (nearly) all lanes busy no matter how
+// many attempts die at the rear rim or at the stop.
+// ------------------------------------------------------------------------------------------------
+constexpr int kPoolSlots = 64;
+constexpr int kWarpsPerCta = 8;
+
+struct alignas(16) WarpPool {
+    float4 film[kPoolSlots];   // fx, fy, max_scale, translation
+    float4 rot[kPoolSlots];    // sn, cs, first lens point (ua, ub)
+    uint4 rng[kPoolSlots];     // per-sample xorshift128 state
+    float4 ray0[kPoolSlots];   // stage A -> B: ox, oy, oz, ux
+    float4 ray1[kPoolSlots];   //               uy, uz, sample index (bits), packed counters (bits)
+    unsigned char qa[kPoolSlots], qb[kPoolSlots], qf[kPoolSlots];
+};
+// packed counters: tries [0..7] | fresh [8] | tir [9..15] | surface visits [16..31]
+__device__ __forceinline__ unsigned pk_tries(unsigned p) { return p & 0xffu; }
+__device__ __forceinline__ bool pk_fresh(unsigned p) { return (p >> 8) & 1u; }
+__device__ __forceinline__ unsigned pk_tir(unsigned p) { return (p >> 9) & 0x7fu; }
+__device__ __forceinline__ unsigned pk_visits(unsigned p) { return p >> 16; }
+
+// surfaces [from, to) of the fused march (see fast_march); `first` = this range starts at surface 0
+template <int kN>
+__device__ __forceinline__ int fast_march_range(const LensState& L, float gscale, int from, int to, float& ox, float& oy,
+                                                float& oz, float& ux, float& uy, float& uz, float dx, float dy, float dz0,
+                                                int* visited) {
+    const float tir_hi = fmaf(1e-4f, gscale, 1.0f), tir_lo = fmaf(-1e-4f, gscale, 1.0f);
+    int n = 0, rc = kPass;
+#pragma unroll
+    for (int i = 0; i < (kN > 0 ? kN : kMaxElements); ++i) {
+        if (i < from) continue;   // warp-uniform
+        if (i >= to) break;       // warp-uniform
+        const Element& e = L.e[i];
+        ++n;
+        const float dz = e.vertex - oz;
+        const float Lz = e.center - oz;
+        const float b = fmaf(ox, ux, oy * uy);
+        const float tca = fmaf(Lz, uz, -b);
+        const float C = fmaf(dz, dz - 2.0f * e.radius, fmaf(ox, ox, oy * oy)) + e.r2_corr;
+        const float disc = fmaf(tca, tca, -C);
+        const float tiny = 1e-5f * gscale * e.radius2;
+        const float s = e.sgn * approx_sqrt(fmaxf(disc, 0.0f));
+        const float t_conj = C * approx_rcp(tca - s);
+        const float t = (tca * s < 0.0f) ? t_conj : tca + s;
+        const float hx = fmaf(ux, t, ox), hy = fmaf(uy, t, oy), hz = fmaf(uz, t, oz);
+        const float h2 = fmaf(hx, hx, hy * hy);
+        const float w = fmaf(hx, ux, hy * uy);
+        const float margin = h2 - e.rim2;
+        const float guard = fmaf(fabsf(w), e.dt_guard, e.rim2_guard);
+        const bool blocked = (disc < -tiny) || (margin > guard);
+        const bool unsure = (margin > -guard) || (disc < tiny);
+        if (blocked || unsure) {
+            rc = blocked ? kBlocked : kUndecided;
+            if (i == 0) { ux = dx; uy = dy; uz = dz0; }
+            break;
+        }
+        const float nzr = e.center - hz;
+        const float c1 = (w - uz * nzr) * e.inv_radius;
+        const float cs2 = fmaf(-e.eta2 * c1, c1, e.eta2);
+        const float k = fmaf(e.eta, c1, -approx_sqrt(fabsf(1.0f - cs2)));
+        const float kk = k * e.inv_radius;
+        ox = hx; oy = hy; oz = hz;
+        if (cs2 > tir_lo) {
+            rc = cs2 > tir_hi ? kTir : kUndecided;
+            if (i == 0) { ux = dx; uy = dy; uz = dz0; }
+            break;
+        }
+        ux = fmaf(kk, -hx, e.eta * ux);
+        uy = fmaf(kk, -hy, e.eta * uy);
+        uz = fmaf(kk, nzr, e.eta * uz);
+    }
+    *visited = n;
+    return rc;
+}
+
+template <int kN, bool kImage, bool kLut>
+__global__ void __launch_bounds__(kWarpsPerCta * 32, 3)
+kolb_pool_kernel(const __grid_constant__ CameraState cam, const float4* __restrict__ samples, uint32_t n,
+                 uint64_t first_index, uint64_t seed, float4* __restrict__ origin_w, float4* __restrict__ dir_tries,
+                 DeviceStats* stats, unsigned long long* chunk_counter, unsigned long long* queue,
+                 unsigned long long* queue_count, unsigned long long capacity, uint64_t queue_base) {
+    __shared__ WarpPool pools[kWarpsPerCta];
+    BokehView bk;
+    if (kImage) bk = stage_bokeh(cam);
+    const LensState& L = cam.lens;
+    const int count = kN > 0 ? kN : L.count;
+    const int split = L.split;
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    WarpPool& P = pools[threadIdx.x >> 5];
+    LocalStats ls = {0, 0, 0, 0, 0, 0, 0};
+    P.qf[lane] = (unsigned char)lane;
+    P.qf[lane + 32] = (unsigned char)(lane + 32);
+    __syncwarp();
+    int nA = 0, nB = 0, nF = kPoolSlots;   // warp-uniform stack heights
+    uint32_t cur = 0, end = 0;
+    bool exhausted = false;
+
+    // push `slot` of every lane with `p` set onto a stack; returns the new height
+    auto push = [&](unsigned char* stack, int height, bool p, int slot) {
+        const unsigned m = __ballot_sync(0xffffffffu, p);
+        if (p) stack[height + __popc(m & lt_mask)] = (unsigned char)slot;
+        return height + __popc(m);
+    };
+    // a finished or abandoned sample: counters, outputs, exact re-run queue
+    auto finish = [&](bool done, bool undecided, uint32_t idx, unsigned packed, float ox, float oy, float oz, float ux,
+                      float uy, float uz) {
+        if (done) {
+            const unsigned tries = pk_tries(packed);
+            float weight = 1.0f;
+            if (tries > (unsigned)kMaxTries) { weight = 0.0f; ls.vignetted++; }
+            else ls.success++;
+            weight *= cam.weight_scale;
+            __stcs(origin_w + idx, make_float4(-ox, -oy, -oz, weight));
+            __stcs(dir_tries + idx, make_float4(-ux, -uy, -uz, (float)tries));
+            ls.rays++;
+            ls.attempts += tries + 1;
+            ls.visits += pk_visits(packed);
+            ls.tir += pk_tir(packed);
+        }
+        const unsigned um = __ballot_sync(0xffffffffu, undecided);
+        if (um) {
+            unsigned long long base = 0;
+            const int leader = __ffs(um) - 1;
+            if ((int)lane == leader) base = atomicAdd(queue_count, (unsigned long long)__popc(um));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (undecided) {
+                const unsigned long long pos = base + __popc(um & lt_mask);
+                if (pos < capacity) {
+                    queue[pos] = queue_base + idx;
+                } else {  // queue full: settle it here, exactly
+                    float4 o4, d4;
+                    kolb_exact_sample<kImage, kLut>(cam, bk, samples[idx], first_index + idx, seed, &o4, &d4, ls);
+                    __stcs(origin_w + idx, o4);
+                    __stcs(dir_tries + idx, d4);
+                    ls.reruns++;
+                }
+            }
+        }
+    };
+
+    for (;;) {
+        const bool more = !exhausted || cur < end;
+        if (nB >= 32 || (nB > 0 && nA == 0 && !more)) {
+            // ---------------- stage B: surfaces [split, count) for up to 32 survivors of stage A
+            const int m = nB < 32 ? nB : 32;
+            const bool act = (int)lane < m;
+            const int slot = act ? P.qb[nB - 1 - lane] : 0;
+            nB -= m;
+            float4 r0 = make_float4(0, 0, 0, 0), r1 = make_float4(0, 0, 1, 0);
+            if (act) { r0 = P.ray0[slot]; r1 = P.ray1[slot]; }
+            float ox = r0.x, oy = r0.y, oz = r0.z, ux = r0.w, uy = r1.x, uz = r1.y;
+            const uint32_t idx = __float_as_uint(r1.z);
+            unsigned packed = __float_as_uint(r1.w);
+            int visited = 0, rc = kPass;
+            if (act) rc = fast_march_range<kN>(L, cam.guard_scale, split, count, ox, oy, oz, ux, uy, uz, 0.f, 0.f, 0.f, &visited);
+            packed += (unsigned)visited << 16;
+            if (rc == kTir) packed += 1u << 9;
+            const bool failed = act && (rc == kBlocked || rc == kTir);
+            const bool again = failed && pk_tries(packed) <= (unsigned)kMaxTries;
+            const bool done = act && (rc == kPass || (failed && !again));
+            const bool undecided = act && rc == kUndecided;
+            if (again) P.ray1[slot].w = __uint_as_float(packed);
+            finish(done, undecided, idx, packed, ox, oy, oz, ux, uy, uz);
+            nA = push(P.qa, nA, again, slot);
+            nF = push(P.qf, nF, done || undecided, slot);
+            __syncwarp();
+            continue;
+        }
+        if (nA == 0 && !more) break;   // nB == 0 here: everything is finished
+        // ---------------- refill: new samples into free slots until a full pass of 32 is available
+        if (nA < 32 && more && nF > 0) {
+            if (cur == end) {
+                unsigned long long base = 0;
+                if (lane == 0) base = atomicAdd(chunk_counter, (unsigned long long)kChunk);
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (base >= n) { exhausted = true; }
+                else { cur = (uint32_t)base; end = (base + kChunk < n) ? (uint32_t)(base + kChunk) : n; }
+            }
+            int take = 32 - nA;
+            if (take > nF) take = nF;
+            if (take > (int)(end - cur)) take = (int)(end - cur);
+            if ((int)lane < take) {
+                const int slot = P.qf[nF - 1 - lane];
+                const uint32_t idx = cur + lane;
+                const float4 s = __ldcs(samples + idx);
+                const KolbSampleState k = kolb_sample_setup<kLut, false>(L, s.x, s.y);
+                const Xor128 g = sample_stream(seed, first_index + idx);
+                P.film[slot] = make_float4(k.fx, k.fy, k.max_scale, k.translation);
+                P.rot[slot] = make_float4(k.sn, k.cs, s.z, s.w);
+                P.rng[slot] = make_uint4(g.x, g.y, g.z, g.w);
+                P.ray1[slot] = make_float4(0.0f, 0.0f, __uint_as_float(idx), __uint_as_float(1u << 8));  // fresh, tries 0
+                P.qa[nA + lane] = (unsigned char)slot;
+            }
+            nF -= take;
+            nA += take;
+            cur += take;
+            __syncwarp();
+        }
+        if (nA == 0) continue;
+        {
+            // ---------------- stage A: lens point, aim, surfaces [0, split) for up to 32 slots
+            const int m = nA < 32 ? nA : 32;
+            const bool act = (int)lane < m;
+            const int slot = act ? P.qa[nA - 1 - lane] : 0;
+            nA -= m;
+            float4 f = make_float4(0, 0, 1, 0), rt = make_float4(0, 1, 0.5f, 0.25f), r1 = make_float4(0, 0, 0, 0);
+            uint4 g4 = make_uint4(1, 2, 3, 4);
+            if (act) { f = P.film[slot]; rt = P.rot[slot]; g4 = P.rng[slot]; r1 = P.ray1[slot]; }
+            const uint32_t idx = __float_as_uint(r1.z);
+            unsigned packed = __float_as_uint(r1.w);
+            const bool fresh = pk_fresh(packed);
+            float ua = rt.z, ub = rt.w;
+            if (!fresh) {
+                Xor128 g = {g4.x, g4.y, g4.z, g4.w};
+                draw_pair(g, &ua, &ub);
+                g4 = make_uint4(g.x, g.y, g.z, g.w);
+                packed += 1u;  // ++tries
+            }
+            packed &= ~(1u << 8);
+            float lx, ly;
+            lens_sample_fast<kImage>(bk, ua, ub, &lx, &ly);
+            KolbSampleState k;
+            k.fx = f.x; k.fy = f.y; k.max_scale = f.z; k.translation = f.w; k.sn = rt.x; k.cs = rt.y;
+            const Vec3 d = kolb_aim<kLut>(L, k, lx, ly, !fresh);
+            const float q = fmaf(d.x, d.x, fmaf(d.y, d.y, d.z * d.z));
+            float y = approx_rsqrt(q);
+            y = y * fmaf(-0.5f * q * y, y, 1.5f);
+            float ox = k.fx, oy = k.fy, oz = L.origin_shift, ux = d.x * y, uy = d.y * y, uz = d.z * y;
+            int visited = 0, rc = kPass;
+            if (act) rc = fast_march_range<kN>(L, cam.guard_scale, 0, split, ox, oy, oz, ux, uy, uz, d.x, d.y, d.z, &visited);
+            packed += (unsigned)visited << 16;
+            if (rc == kTir) packed += 1u << 9;
+            const bool failed = act && (rc == kBlocked || rc == kTir);
+            const bool again = failed && pk_tries(packed) <= (unsigned)kMaxTries;
+            const bool onward = act && rc == kPass;
+            const bool done = failed && !again;
+            const bool undecided = act && rc == kUndecided;
+            if (again || onward) {
+                if (!fresh) P.rng[slot] = g4;
+                if (onward) P.ray0[slot] = make_float4(ox, oy, oz, ux);
+                P.ray1[slot] = make_float4(uy, uz, __uint_as_float(idx), __uint_as_float(packed));
+            }
+            finish(done, undecided, idx, packed, ox, oy, oz, ux, uy, uz);
+            nA = push(P.qa, nA, again, slot);
+            nB = push(P.qb, nB, onward, slot);
+            nF = push(P.qf, nF, done || undecided, slot);
+            __syncwarp();
+        }
+    }
+    flush_stats(ls, stats);
+}
+
+// ------------------------------------------------------------------------------------------------
 // Thin lens with optical vignetting: the same persistent-warp / per-lane regeneration schedule, EXACT
 // arithmetic (the thin-lens attempt has no double-precision step, so exactness costs little): results are
 // bit-identical to thin_exact_sample, only the order of work differs.
@@ -708,6 +926,39 @@ static cudaError_t launch_variant(const CameraState& cam, int mode, const float4
         cudaError_t e = cudaMemsetAsync(ws.counters, 0, 2 * sizeof(unsigned long long), st);
         if (e != cudaSuccess) return e;
         const unsigned grid = (unsigned)sm_count() * 3;  // persistent: 3 CTAs of 8 warps per SM
+        static const bool use_v2 = getenv("ZOICB_KOLB_V2") != nullptr;  // A/B switch for the single-stage schedule
+        if (!use_v2) {
+            // two-stage pool kernel; 32-bit sample offsets inside a launch, so very large batches go in slices
+            const uint64_t slice = 1ull << 31;
+            for (uint64_t b = 0; b < n; b += slice) {
+                const uint32_t m = (uint32_t)((n - b < slice) ? n - b : slice);
+                if (b) {
+                    e = cudaMemsetAsync(ws.counters, 0, sizeof(unsigned long long), st);  // chunk cursor only
+                    if (e != cudaSuccess) return e;
+                }
+#define ZP(N)                                                                                                            \
+    do {                                                                                                                 \
+        if (smem) cudaFuncSetAttribute(kolb_pool_kernel<N, kImage, kLut>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        kolb_pool_kernel<N, kImage, kLut><<<grid, threads, smem, st>>>(cam, samples + b, m, first_index + b, seed, origin_w + b,   \
+                                                                      dir_tries + b, stats, ws.counters, ws.queue,       \
+                                                                      ws.counters + 1, ws.capacity, b);                  \
+    } while (0)
+                switch (cam.lens.count) {
+                    case 7: ZP(7); break;
+                    case 8: ZP(8); break;
+                    case 9: ZP(9); break;
+                    case 11: ZP(11); break;
+                    case 12: ZP(12); break;
+                    default: ZP(0); break;
+                }
+#undef ZP
+                if (launches) *launches += 1;
+            }
+            rerun_kernel<kModel, kImage, kLut><<<(unsigned)sm_count() * 2, threads, smem, st>>>(
+                cam, samples, first_index, seed, origin_w, dir_tries, stats, stage, ws.queue, ws.counters + 1, ws.capacity);
+            if (launches) *launches += 1;
+            return cudaGetLastError();
+        }
 #define ZG(N) kolb_guarded_kernel<N, kImage, kLut><<<grid, threads, smem, st>>>(cam, samples, n, first_index, seed, origin_w, \
                                                                          dir_tries, stats, stage, ws.counters, ws.queue,   \
                                                                          ws.counters + 1, ws.capacity)
