@@ -33,7 +33,8 @@ struct Element {
     float vertex;          // z where the sphere the REFERENCE intersects (centre fl(z - R), radius^2 fl(R*R))
                            // crosses the axis: fl(center + R)
     float r2_corr;         // R*R - fl(R*R) evaluated in double: |o-c|^2 - radius2 = dz*(dz-2R) + ox^2+oy^2 + r2_corr
-    float pad0, pad1, pad2;
+    float miss_guard;      // 1e-5 * radius2: |discriminant| below this => the hit/miss test is undecided
+    float pad1, pad2;
 };
 
 struct LensState {

@@ -221,14 +221,16 @@ zoicb_status zoicb_set_guard_scale(zoicb_ctx* ctx, float scale) {
         for (int i = 0; i < kMaxElements; ++i) {
             ctx->base_guards.push_back(ctx->host.state.lens.e[i].rim2_guard);
             ctx->base_guards.push_back(ctx->host.state.lens.e[i].dt_guard);
+            ctx->base_guards.push_back(ctx->host.state.lens.e[i].miss_guard);
         }
         ctx->base_guards.push_back(ctx->host.state.thin.ov_guard);
     }
     for (int i = 0; i < kMaxElements; ++i) {
-        ctx->host.state.lens.e[i].rim2_guard = ctx->base_guards[2 * i] * scale;
-        ctx->host.state.lens.e[i].dt_guard = ctx->base_guards[2 * i + 1] * scale;
+        ctx->host.state.lens.e[i].rim2_guard = ctx->base_guards[3 * i] * scale;
+        ctx->host.state.lens.e[i].dt_guard = ctx->base_guards[3 * i + 1] * scale;
+        ctx->host.state.lens.e[i].miss_guard = ctx->base_guards[3 * i + 2] * scale;
     }
-    ctx->host.state.thin.ov_guard = ctx->base_guards[2 * kMaxElements] * scale;
+    ctx->host.state.thin.ov_guard = ctx->base_guards[3 * kMaxElements] * scale;
     ctx->host.state.guard_scale = scale;
     return ZOICB_OK;
 }

@@ -494,7 +494,7 @@ kolb_guarded_kernel(const __grid_constant__ CameraState cam, const float4* __res
 // 32 slots from whichever stack is full enough, so both stages run with (nearly) all lanes busy no matter how
 // many attempts die at the rear rim or at the stop.
 // ------------------------------------------------------------------------------------------------
-constexpr int kPoolSlots = 64;
+constexpr int kPoolSlots = 96;   // 3 x 32: one of the three stacks always holds a full pass (pigeonhole)
 constexpr int kWarpsPerCta = 8;
 
 struct alignas(16) WarpPool {
@@ -511,26 +511,24 @@ __device__ __forceinline__ bool pk_fresh(unsigned p) { return (p >> 8) & 1u; }
 __device__ __forceinline__ unsigned pk_tir(unsigned p) { return (p >> 9) & 0x7fu; }
 __device__ __forceinline__ unsigned pk_visits(unsigned p) { return p >> 16; }
 
-// surfaces [from, to) of the fused march (see fast_march); `first` = this range starts at surface 0
+// surfaces [from, to) of the fused march (same arithmetic as fast_march); from/to are warp-uniform
 template <int kN>
 __device__ __forceinline__ int fast_march_range(const LensState& L, float gscale, int from, int to, float& ox, float& oy,
                                                 float& oz, float& ux, float& uy, float& uz, float dx, float dy, float dz0,
                                                 int* visited) {
     const float tir_hi = fmaf(1e-4f, gscale, 1.0f), tir_lo = fmaf(-1e-4f, gscale, 1.0f);
-    int n = 0, rc = kPass;
+    int last = to - 1, rc = kPass;   // index of the last surface entered
 #pragma unroll
     for (int i = 0; i < (kN > 0 ? kN : kMaxElements); ++i) {
         if (i < from) continue;   // warp-uniform
         if (i >= to) break;       // warp-uniform
         const Element& e = L.e[i];
-        ++n;
         const float dz = e.vertex - oz;
         const float Lz = e.center - oz;
         const float b = fmaf(ox, ux, oy * uy);
         const float tca = fmaf(Lz, uz, -b);
         const float C = fmaf(dz, dz - 2.0f * e.radius, fmaf(ox, ox, oy * oy)) + e.r2_corr;
         const float disc = fmaf(tca, tca, -C);
-        const float tiny = 1e-5f * gscale * e.radius2;
         const float s = e.sgn * approx_sqrt(fmaxf(disc, 0.0f));
         const float t_conj = C * approx_rcp(tca - s);
         const float t = (tca * s < 0.0f) ? t_conj : tca + s;
@@ -539,11 +537,11 @@ __device__ __forceinline__ int fast_march_range(const LensState& L, float gscale
         const float w = fmaf(hx, ux, hy * uy);
         const float margin = h2 - e.rim2;
         const float guard = fmaf(fabsf(w), e.dt_guard, e.rim2_guard);
-        const bool blocked = (disc < -tiny) || (margin > guard);
-        const bool unsure = (margin > -guard) || (disc < tiny);
-        if (blocked || unsure) {
+        if (margin > -guard || disc < e.miss_guard) {   // stopped here, or too close to call
+            const bool blocked = (disc < -e.miss_guard) || (margin > guard);
             rc = blocked ? kBlocked : kUndecided;
             if (i == 0) { ux = dx; uy = dy; uz = dz0; }
+            last = i;
             break;
         }
         const float nzr = e.center - hz;
@@ -555,13 +553,14 @@ __device__ __forceinline__ int fast_march_range(const LensState& L, float gscale
         if (cs2 > tir_lo) {
             rc = cs2 > tir_hi ? kTir : kUndecided;
             if (i == 0) { ux = dx; uy = dy; uz = dz0; }
+            last = i;
             break;
         }
         ux = fmaf(kk, -hx, e.eta * ux);
         uy = fmaf(kk, -hy, e.eta * uy);
         uz = fmaf(kk, nzr, e.eta * uz);
     }
-    *visited = n;
+    *visited = last - from + 1;
     return rc;
 }
 
@@ -571,18 +570,20 @@ kolb_pool_kernel(const __grid_constant__ CameraState cam, const float4* __restri
                  uint64_t first_index, uint64_t seed, float4* __restrict__ origin_w, float4* __restrict__ dir_tries,
                  DeviceStats* stats, unsigned long long* chunk_counter, unsigned long long* queue,
                  unsigned long long* queue_count, unsigned long long capacity, uint64_t queue_base) {
-    __shared__ WarpPool pools[kWarpsPerCta];
+    // dynamic shared memory: [bokeh row tables (2h floats, 16-byte aligned)] [one WarpPool per warp]
     BokehView bk;
     if (kImage) bk = stage_bokeh(cam);
+    const unsigned rows_bytes = kImage ? ((unsigned)cam.bokeh.h * 8u + 15u) & ~15u : 0u;
+    WarpPool& P = reinterpret_cast<WarpPool*>(reinterpret_cast<char*>(s_rows) + rows_bytes)[threadIdx.x >> 5];
     const LensState& L = cam.lens;
     const int count = kN > 0 ? kN : L.count;
     const int split = L.split;
     const unsigned lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
-    WarpPool& P = pools[threadIdx.x >> 5];
     LocalStats ls = {0, 0, 0, 0, 0, 0, 0};
     P.qf[lane] = (unsigned char)lane;
     P.qf[lane + 32] = (unsigned char)(lane + 32);
+    P.qf[lane + 64] = (unsigned char)(lane + 64);
     __syncwarp();
     int nA = 0, nB = 0, nF = kPoolSlots;   // warp-uniform stack heights
     uint32_t cur = 0, end = 0;
@@ -632,45 +633,28 @@ kolb_pool_kernel(const __grid_constant__ CameraState cam, const float4* __restri
     };
 
     for (;;) {
+        // ---------------- pick the next pass: a full warp of work from one of the stacks whenever there is one
         const bool more = !exhausted || cur < end;
-        if (nB >= 32 || (nB > 0 && nA == 0 && !more)) {
-            // ---------------- stage B: surfaces [split, count) for up to 32 survivors of stage A
-            const int m = nB < 32 ? nB : 32;
-            const bool act = (int)lane < m;
-            const int slot = act ? P.qb[nB - 1 - lane] : 0;
-            nB -= m;
-            float4 r0 = make_float4(0, 0, 0, 0), r1 = make_float4(0, 0, 1, 0);
-            if (act) { r0 = P.ray0[slot]; r1 = P.ray1[slot]; }
-            float ox = r0.x, oy = r0.y, oz = r0.z, ux = r0.w, uy = r1.x, uz = r1.y;
-            const uint32_t idx = __float_as_uint(r1.z);
-            unsigned packed = __float_as_uint(r1.w);
-            int visited = 0, rc = kPass;
-            if (act) rc = fast_march_range<kN>(L, cam.guard_scale, split, count, ox, oy, oz, ux, uy, uz, 0.f, 0.f, 0.f, &visited);
-            packed += (unsigned)visited << 16;
-            if (rc == kTir) packed += 1u << 9;
-            const bool failed = act && (rc == kBlocked || rc == kTir);
-            const bool again = failed && pk_tries(packed) <= (unsigned)kMaxTries;
-            const bool done = act && (rc == kPass || (failed && !again));
-            const bool undecided = act && rc == kUndecided;
-            if (again) P.ray1[slot].w = __uint_as_float(packed);
-            finish(done, undecided, idx, packed, ox, oy, oz, ux, uy, uz);
-            nA = push(P.qa, nA, again, slot);
-            nF = push(P.qf, nF, done || undecided, slot);
-            __syncwarp();
-            continue;
-        }
-        if (nA == 0 && !more) break;   // nB == 0 here: everything is finished
-        // ---------------- refill: new samples into free slots until a full pass of 32 is available
-        if (nA < 32 && more && nF > 0) {
+        int mode, m = 32;   // mode 0: stage B, 1: stage A, 2: take new samples
+        if (nB >= 32) mode = 0;
+        else if (nA >= 32) mode = 1;
+        else if (more && nF >= 32) mode = 2;
+        else if (nB > 0) { mode = 0; m = nB; }      // the tail of the launch: partial passes
+        else if (nA > 0) { mode = 1; m = nA; }
+        else if (more) mode = 2;
+        else break;
+
+        if (mode == 2) {
+            // ---------------- new samples: per-sample set-up (film point, LUT, rotation, retry stream) into free slots
             if (cur == end) {
                 unsigned long long base = 0;
                 if (lane == 0) base = atomicAdd(chunk_counter, (unsigned long long)kChunk);
                 base = __shfl_sync(0xffffffffu, base, 0);
-                if (base >= n) { exhausted = true; }
-                else { cur = (uint32_t)base; end = (base + kChunk < n) ? (uint32_t)(base + kChunk) : n; }
+                if (base >= n) { exhausted = true; continue; }
+                cur = (uint32_t)base;
+                end = (base + kChunk < n) ? (uint32_t)(base + kChunk) : n;
             }
-            int take = 32 - nA;
-            if (take > nF) take = nF;
+            int take = nF < 32 ? nF : 32;
             if (take > (int)(end - cur)) take = (int)(end - cur);
             if ((int)lane < take) {
                 const int slot = P.qf[nF - 1 - lane];
@@ -688,11 +672,33 @@ kolb_pool_kernel(const __grid_constant__ CameraState cam, const float4* __restri
             nA += take;
             cur += take;
             __syncwarp();
-        }
-        if (nA == 0) continue;
-        {
-            // ---------------- stage A: lens point, aim, surfaces [0, split) for up to 32 slots
-            const int m = nA < 32 ? nA : 32;
+        } else if (mode == 0) {
+            // ---------------- stage B: surfaces [split, count) for survivors of stage A
+            const bool act = (int)lane < m;
+            const int slot = act ? P.qb[nB - 1 - lane] : 0;
+            nB -= m;
+            float4 r0 = make_float4(0, 0, 0, 0), r1 = make_float4(0, 0, 1, 0);
+            if (act) { r0 = P.ray0[slot]; r1 = P.ray1[slot]; }
+            float ox = r0.x, oy = r0.y, oz = r0.z, ux = r0.w, uy = r1.x, uz = r1.y;
+            const uint32_t idx = __float_as_uint(r1.z);
+            unsigned packed = __float_as_uint(r1.w);
+            int visited = 0, rc = kPass;
+            if (act) {
+                rc = fast_march_range<kN>(L, cam.guard_scale, split, count, ox, oy, oz, ux, uy, uz, 0.f, 0.f, 0.f, &visited);
+                packed += (unsigned)visited << 16;
+                if (rc == kTir) packed += 1u << 9;
+            }
+            const bool failed = act && (rc == kBlocked || rc == kTir);
+            const bool again = failed && pk_tries(packed) <= (unsigned)kMaxTries;
+            const bool done = act && (rc == kPass || (failed && !again));
+            const bool undecided = act && rc == kUndecided;
+            if (again) P.ray1[slot].w = __uint_as_float(packed);
+            finish(done, undecided, idx, packed, ox, oy, oz, ux, uy, uz);
+            nA = push(P.qa, nA, again, slot);
+            nF = push(P.qf, nF, done || undecided, slot);
+            __syncwarp();
+        } else {
+            // ---------------- stage A: lens point, aim, surfaces [0, split)
             const bool act = (int)lane < m;
             const int slot = act ? P.qa[nA - 1 - lane] : 0;
             nA -= m;
@@ -720,9 +726,11 @@ kolb_pool_kernel(const __grid_constant__ CameraState cam, const float4* __restri
             y = y * fmaf(-0.5f * q * y, y, 1.5f);
             float ox = k.fx, oy = k.fy, oz = L.origin_shift, ux = d.x * y, uy = d.y * y, uz = d.z * y;
             int visited = 0, rc = kPass;
-            if (act) rc = fast_march_range<kN>(L, cam.guard_scale, 0, split, ox, oy, oz, ux, uy, uz, d.x, d.y, d.z, &visited);
-            packed += (unsigned)visited << 16;
-            if (rc == kTir) packed += 1u << 9;
+            if (act) {
+                rc = fast_march_range<kN>(L, cam.guard_scale, 0, split, ox, oy, oz, ux, uy, uz, d.x, d.y, d.z, &visited);
+                packed += (unsigned)visited << 16;
+                if (rc == kTir) packed += 1u << 9;
+            }
             const bool failed = act && (rc == kBlocked || rc == kTir);
             const bool again = failed && pk_tries(packed) <= (unsigned)kMaxTries;
             const bool onward = act && rc == kPass;
@@ -938,8 +946,9 @@ static cudaError_t launch_variant(const CameraState& cam, int mode, const float4
                 }
 #define ZP(N)                                                                                                            \
     do {                                                                                                                 \
-        if (smem) cudaFuncSetAttribute(kolb_pool_kernel<N, kImage, kLut>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-        kolb_pool_kernel<N, kImage, kLut><<<grid, threads, smem, st>>>(cam, samples + b, m, first_index + b, seed, origin_w + b,   \
+        const size_t pool_smem = ((smem + 15) & ~(size_t)15) + kWarpsPerCta * sizeof(WarpPool);                            \
+        cudaFuncSetAttribute(kolb_pool_kernel<N, kImage, kLut>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pool_smem);      \
+        kolb_pool_kernel<N, kImage, kLut><<<grid, threads, pool_smem, st>>>(cam, samples + b, m, first_index + b, seed, origin_w + b, \
                                                                       dir_tries + b, stats, ws.counters, ws.queue,       \
                                                                       ws.counters + 1, ws.capacity, b);                  \
     } while (0)
