@@ -34,7 +34,8 @@ struct Element {
                            // crosses the axis: fl(center + R)
     float r2_corr;         // R*R - fl(R*R) evaluated in double: |o-c|^2 - radius2 = dz*(dz-2R) + ox^2+oy^2 + r2_corr
     float miss_guard;      // 1e-5 * radius2: |discriminant| below this => the hit/miss test is undecided
-    float pad1, pad2;
+    float vertex_m2r;      // vertex - 2R
+    float pad2;
 };
 
 struct LensState {

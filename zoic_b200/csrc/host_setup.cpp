@@ -248,7 +248,8 @@ void pack_elements(const std::vector<LensRow>& rows, int stop, float user_radius
         e.dt_guard = 2.0f * (8.0f * 5.9604645e-8f * (fabsf(e.radius) + len));
         e.rim2_guard = 2.0f * sqrtf(T) * (4e-6f * fmaxf(len, 2.0f));
         e.miss_guard = 1e-5f * e.radius2;
-        e.pad1 = e.pad2 = 0.0f;
+        e.vertex_m2r = (float)((double)e.center - (double)e.radius);
+        e.pad2 = 0.0f;
     }
 }
 

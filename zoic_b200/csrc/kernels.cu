@@ -511,55 +511,53 @@ __device__ __forceinline__ bool pk_fresh(unsigned p) { return (p >> 8) & 1u; }
 __device__ __forceinline__ unsigned pk_tir(unsigned p) { return (p >> 9) & 0x7fu; }
 __device__ __forceinline__ unsigned pk_visits(unsigned p) { return p >> 16; }
 
-// surfaces [from, to) of the fused march (same arithmetic as fast_march); from/to are warp-uniform
+// surfaces [from, to) of the fused march (same arithmetic as fast_march); from/to are warp-uniform.
+// A ray that is stopped leaves with its state DEAD (nothing after the loop reads o/u of a stopped ray), which
+// lets the compiler keep the unrolled surfaces in straight-line SSA form without copies at the exits.
 template <int kN>
 __device__ __forceinline__ int fast_march_range(const LensState& L, float gscale, int from, int to, float& ox, float& oy,
-                                                float& oz, float& ux, float& uy, float& uz, float dx, float dy, float dz0,
-                                                int* visited) {
+                                                float& oz, float& ux, float& uy, float& uz, int* visited) {
     const float tir_hi = fmaf(1e-4f, gscale, 1.0f), tir_lo = fmaf(-1e-4f, gscale, 1.0f);
     int last = to - 1, rc = kPass;   // index of the last surface entered
+    float px = ox, py = oy, pz = oz, vx = ux, vy = uy, vz = uz;
 #pragma unroll
     for (int i = 0; i < (kN > 0 ? kN : kMaxElements); ++i) {
         if (i < from) continue;   // warp-uniform
         if (i >= to) break;       // warp-uniform
         const Element& e = L.e[i];
-        const float dz = e.vertex - oz;
-        const float Lz = e.center - oz;
-        const float b = fmaf(ox, ux, oy * uy);
-        const float tca = fmaf(Lz, uz, -b);
-        const float C = fmaf(dz, dz - 2.0f * e.radius, fmaf(ox, ox, oy * oy)) + e.r2_corr;
+        const float dz = e.vertex - pz;
+        const float m2 = e.vertex_m2r - pz;                              // dz - 2R
+        const float Lz = e.center - pz;
+        const float tca = fmaf(Lz, vz, -fmaf(px, vx, py * vy));
+        // C = |o - c|^2 - radius2 = dz (dz - 2R) + ox^2 + oy^2 + (R^2 - fl(R^2))
+        const float C = fmaf(dz, m2, fmaf(px, px, fmaf(py, py, e.r2_corr)));
         const float disc = fmaf(tca, tca, -C);
         const float s = e.sgn * approx_sqrt(fmaxf(disc, 0.0f));
-        const float t_conj = C * approx_rcp(tca - s);
-        const float t = (tca * s < 0.0f) ? t_conj : tca + s;
-        const float hx = fmaf(ux, t, ox), hy = fmaf(uy, t, oy), hz = fmaf(uz, t, oz);
-        const float h2 = fmaf(hx, hx, hy * hy);
-        const float w = fmaf(hx, ux, hy * uy);
-        const float margin = h2 - e.rim2;
+        const float t = (tca * s < 0.0f) ? C * approx_rcp(tca - s) : tca + s;   // conjugate root when tca + s cancels
+        const float hx = fmaf(vx, t, px), hy = fmaf(vy, t, py), hz = fmaf(vz, t, pz);
+        const float w = fmaf(hx, vx, hy * vy);
+        const float margin = fmaf(hx, hx, fmaf(hy, hy, -e.rim2));
         const float guard = fmaf(fabsf(w), e.dt_guard, e.rim2_guard);
         if (margin > -guard || disc < e.miss_guard) {   // stopped here, or too close to call
-            const bool blocked = (disc < -e.miss_guard) || (margin > guard);
-            rc = blocked ? kBlocked : kUndecided;
-            if (i == 0) { ux = dx; uy = dy; uz = dz0; }
+            rc = ((disc < -e.miss_guard) || (margin > guard)) ? kBlocked : kUndecided;
             last = i;
             break;
         }
         const float nzr = e.center - hz;
-        const float c1 = (w - uz * nzr) * e.inv_radius;
+        const float c1 = (w - vz * nzr) * e.inv_radius;
         const float cs2 = fmaf(-e.eta2 * c1, c1, e.eta2);
-        const float k = fmaf(e.eta, c1, -approx_sqrt(fabsf(1.0f - cs2)));
-        const float kk = k * e.inv_radius;
-        ox = hx; oy = hy; oz = hz;
         if (cs2 > tir_lo) {
             rc = cs2 > tir_hi ? kTir : kUndecided;
-            if (i == 0) { ux = dx; uy = dy; uz = dz0; }
             last = i;
             break;
         }
-        ux = fmaf(kk, -hx, e.eta * ux);
-        uy = fmaf(kk, -hy, e.eta * uy);
-        uz = fmaf(kk, nzr, e.eta * uz);
+        const float kk = fmaf(e.eta, c1, -approx_sqrt(fabsf(1.0f - cs2))) * e.inv_radius;
+        vx = fmaf(kk, -hx, e.eta * vx);
+        vy = fmaf(kk, -hy, e.eta * vy);
+        vz = fmaf(kk, nzr, e.eta * vz);
+        px = hx; py = hy; pz = hz;
     }
+    if (rc == kPass) { ox = px; oy = py; oz = pz; ux = vx; uy = vy; uz = vz; }
     *visited = last - from + 1;
     return rc;
 }
@@ -595,13 +593,15 @@ kolb_pool_kernel(const __grid_constant__ CameraState cam, const float4* __restri
         if (p) stack[height + __popc(m & lt_mask)] = (unsigned char)slot;
         return height + __popc(m);
     };
-    // a finished or abandoned sample: counters, outputs, exact re-run queue
+    // a finished or abandoned sample: counters, outputs, exact re-run queue.  A sample that ran out of retries
+    // gets weight 0 and -- its half-traced state being meaningless in the reference too --
+    // the film point as origin and the optical axis as direction.
     auto finish = [&](bool done, bool undecided, uint32_t idx, unsigned packed, float ox, float oy, float oz, float ux,
                       float uy, float uz) {
         if (done) {
             const unsigned tries = pk_tries(packed);
             float weight = 1.0f;
-            if (tries > (unsigned)kMaxTries) { weight = 0.0f; ls.vignetted++; }
+            if (tries > (unsigned)kMaxTries) { weight = 0.0f; ls.vignetted++; ux = 0.0f; uy = 0.0f; uz = 1.0f; }
             else ls.success++;
             weight *= cam.weight_scale;
             __stcs(origin_w + idx, make_float4(-ox, -oy, -oz, weight));
@@ -684,7 +684,7 @@ kolb_pool_kernel(const __grid_constant__ CameraState cam, const float4* __restri
             unsigned packed = __float_as_uint(r1.w);
             int visited = 0, rc = kPass;
             if (act) {
-                rc = fast_march_range<kN>(L, cam.guard_scale, split, count, ox, oy, oz, ux, uy, uz, 0.f, 0.f, 0.f, &visited);
+                rc = fast_march_range<kN>(L, cam.guard_scale, split, count, ox, oy, oz, ux, uy, uz, &visited);
                 packed += (unsigned)visited << 16;
                 if (rc == kTir) packed += 1u << 9;
             }
@@ -727,7 +727,7 @@ kolb_pool_kernel(const __grid_constant__ CameraState cam, const float4* __restri
             float ox = k.fx, oy = k.fy, oz = L.origin_shift, ux = d.x * y, uy = d.y * y, uz = d.z * y;
             int visited = 0, rc = kPass;
             if (act) {
-                rc = fast_march_range<kN>(L, cam.guard_scale, 0, split, ox, oy, oz, ux, uy, uz, d.x, d.y, d.z, &visited);
+                rc = fast_march_range<kN>(L, cam.guard_scale, 0, split, ox, oy, oz, ux, uy, uz, &visited);
                 packed += (unsigned)visited << 16;
                 if (rc == kTir) packed += 1u << 9;
             }
