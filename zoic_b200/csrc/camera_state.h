@@ -35,7 +35,7 @@ struct Element {
     float r2_corr;         // R*R - fl(R*R) evaluated in double: |o-c|^2 - radius2 = dz*(dz-2R) + ox^2+oy^2 + r2_corr
     float miss_guard;      // 1e-5 * radius2: |discriminant| below this => the hit/miss test is undecided
     float vertex_m2r;      // vertex - 2R
-    float pad2;
+    float one_m_eta2;      // fl(1 - eta^2) evaluated in double: 1 - cs2 = (1 - eta^2) + eta^2 c1^2 in one fma
 };
 
 struct LensState {

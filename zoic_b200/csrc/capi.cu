@@ -94,12 +94,12 @@ bool lut_trace_gpu(void* user, const LensState& lens, const float* film_x, int n
     return ok;
 }
 
-// Scratch for the guarded mode on `st`, large enough for n samples: room for n/64 undecided samples
-// (measured rates are 1e-4 .. 3e-3); anything beyond the capacity is settled inline by the kernel.
+// Scratch for the guarded mode on `st`, large enough for n samples: room for n/24 undecided samples
+// (measured rates are 1e-4 .. 1.7e-2); anything beyond the capacity is settled inline by the kernel.
 cudaError_t get_workspace(zoicb_ctx* c, cudaStream_t st, uint64_t n, Workspace* out) {
     std::lock_guard<std::mutex> lock(c->ws_mu);
     Workspace& w = c->workspaces[st];
-    unsigned long long want = n / 64 + 4096;
+    unsigned long long want = n / 24 + 4096;
     if (want > (1ull << 27)) want = 1ull << 27;
     cudaError_t e;
     if (!w.counters) {

@@ -249,7 +249,7 @@ void pack_elements(const std::vector<LensRow>& rows, int stop, float user_radius
         e.rim2_guard = 2.0f * sqrtf(T) * (4e-6f * fmaxf(len, 2.0f));
         e.miss_guard = 1e-5f * e.radius2;
         e.vertex_m2r = (float)((double)e.center - (double)e.radius);
-        e.pad2 = 0.0f;
+        e.one_m_eta2 = (float)(1.0 - (double)e.eta2);
     }
 }
 

@@ -517,7 +517,7 @@ __device__ __forceinline__ unsigned pk_visits(unsigned p) { return p >> 16; }
 template <int kN>
 __device__ __forceinline__ int fast_march_range(const LensState& L, float gscale, int from, int to, float& ox, float& oy,
                                                 float& oz, float& ux, float& uy, float& uz, int* visited) {
-    const float tir_hi = fmaf(1e-4f, gscale, 1.0f), tir_lo = fmaf(-1e-4f, gscale, 1.0f);
+    const float tir_band = 1e-4f * gscale;
     int last = to - 1, rc = kPass;   // index of the last surface entered
     float px = ox, py = oy, pz = oz, vx = ux, vy = uy, vz = uz;
 #pragma unroll
@@ -545,13 +545,13 @@ __device__ __forceinline__ int fast_march_range(const LensState& L, float gscale
         }
         const float nzr = e.center - hz;
         const float c1 = (w - vz * nzr) * e.inv_radius;
-        const float cs2 = fmaf(-e.eta2 * c1, c1, e.eta2);
-        if (cs2 > tir_lo) {
-            rc = cs2 > tir_hi ? kTir : kUndecided;
+        const float rad = fmaf(e.eta2 * c1, c1, e.one_m_eta2);   // 1 - cs2, cs2 = eta^2 (1 - c1^2); negative => TIR
+        if (rad < tir_band) {
+            rc = rad < -tir_band ? kTir : kUndecided;
             last = i;
             break;
         }
-        const float kk = fmaf(e.eta, c1, -approx_sqrt(fabsf(1.0f - cs2))) * e.inv_radius;
+        const float kk = fmaf(e.eta, c1, -approx_sqrt(rad)) * e.inv_radius;
         vx = fmaf(kk, -hx, e.eta * vx);
         vy = fmaf(kk, -hy, e.eta * vy);
         vz = fmaf(kk, nzr, e.eta * vz);
@@ -707,37 +707,44 @@ kolb_pool_kernel(const __grid_constant__ CameraState cam, const float4* __restri
             if (act) { f = P.film[slot]; rt = P.rot[slot]; g4 = P.rng[slot]; r1 = P.ray1[slot]; }
             const uint32_t idx = __float_as_uint(r1.z);
             unsigned packed = __float_as_uint(r1.w);
-            const bool fresh = pk_fresh(packed);
-            float ua = rt.z, ub = rt.w;
-            if (!fresh) {
-                Xor128 g = {g4.x, g4.y, g4.z, g4.w};
-                draw_pair(g, &ua, &ub);
-                g4 = make_uint4(g.x, g.y, g.z, g.w);
-                packed += 1u;  // ++tries
-            }
+            bool fresh = pk_fresh(packed);
             packed &= ~(1u << 8);
-            float lx, ly;
-            lens_sample_fast<kImage>(bk, ua, ub, &lx, &ly);
+            float ua = rt.z, ub = rt.w;
             KolbSampleState k;
             k.fx = f.x; k.fy = f.y; k.max_scale = f.z; k.translation = f.w; k.sn = rt.x; k.cs = rt.y;
-            const Vec3 d = kolb_aim<kLut>(L, k, lx, ly, !fresh);
-            const float q = fmaf(d.x, d.x, fmaf(d.y, d.y, d.z * d.z));
-            float y = approx_rsqrt(q);
-            y = y * fmaf(-0.5f * q * y, y, 1.5f);
-            float ox = k.fx, oy = k.fy, oz = L.origin_shift, ux = d.x * y, uy = d.y * y, uz = d.z * y;
-            int visited = 0, rc = kPass;
-            if (act) {
-                rc = fast_march_range<kN>(L, cam.guard_scale, 0, split, ox, oy, oz, ux, uy, uz, &visited);
-                packed += (unsigned)visited << 16;
-                if (rc == kTir) packed += 1u << 9;
+            Xor128 g = {g4.x, g4.y, g4.z, g4.w};
+            float ox = k.fx, oy = k.fy, oz = L.origin_shift, ux = 0.0f, uy = 0.0f, uz = 1.0f;
+            int rc = kPass;
+            bool todo = act;   // lanes that still owe an attempt in this pass
+            // While at least half the warp was stopped inside stage A, those lanes re-sample right here instead of
+            // going round through the stacks (the cheap path for cameras whose attempts mostly die at the rear rim).
+            for (;;) {
+                if (todo) {
+                    if (!fresh) { draw_pair(g, &ua, &ub); packed += 1u; }   // ++tries
+                    float lx, ly;
+                    lens_sample_fast<kImage>(bk, ua, ub, &lx, &ly);
+                    const Vec3 d = kolb_aim<kLut>(L, k, lx, ly, !fresh);
+                    const float q = fmaf(d.x, d.x, fmaf(d.y, d.y, d.z * d.z));
+                    float y = approx_rsqrt(q);
+                    y = y * fmaf(-0.5f * q * y, y, 1.5f);
+                    ox = k.fx; oy = k.fy; oz = L.origin_shift; ux = d.x * y; uy = d.y * y; uz = d.z * y;
+                    int visited = 0;
+                    rc = fast_march_range<kN>(L, cam.guard_scale, 0, split, ox, oy, oz, ux, uy, uz, &visited);
+                    packed += (unsigned)visited << 16;
+                    if (rc == kTir) packed += 1u << 9;
+                    fresh = false;
+                }
+                todo = todo && (rc == kBlocked || rc == kTir) && pk_tries(packed) <= (unsigned)kMaxTries;
+                if (__popc(__ballot_sync(0xffffffffu, todo)) < 16) break;
             }
+            g4 = make_uint4(g.x, g.y, g.z, g.w);
             const bool failed = act && (rc == kBlocked || rc == kTir);
             const bool again = failed && pk_tries(packed) <= (unsigned)kMaxTries;
             const bool onward = act && rc == kPass;
             const bool done = failed && !again;
             const bool undecided = act && rc == kUndecided;
             if (again || onward) {
-                if (!fresh) P.rng[slot] = g4;
+                P.rng[slot] = g4;
                 if (onward) P.ray0[slot] = make_float4(ox, oy, oz, ux);
                 P.ray1[slot] = make_float4(uy, uz, __uint_as_float(idx), __uint_as_float(packed));
             }
