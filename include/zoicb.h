@@ -103,6 +103,7 @@ typedef struct zoicb_constants {
     float lutKey[ZOICB_LUT_SIZE];
     float lutMinX[ZOICB_LUT_SIZE], lutMinY[ZOICB_LUT_SIZE], lutMaxX[ZOICB_LUT_SIZE], lutMaxY[ZOICB_LUT_SIZE];
     int32_t guardedSplit;   /* surfaces [0, split) / [split, lensCount): the two stages of the guarded kernel */
+    int32_t guardedInnerRetry; /* 1: rays stopped in stage A re-sample inside the pass (high-rejection cameras) */
 } zoicb_constants;
 
 typedef struct zoicb_ctx zoicb_ctx;

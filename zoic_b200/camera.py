@@ -39,7 +39,7 @@ def make_params(**kw):
 def _constants_to_dict(c):
     n, nl = c.lensCount, c.lutSize
     out = {k: getattr(c, k) for k in ("lensCount", "apertureElement", "lutSize", "bokehWidth", "bokehHeight",
-                                      "guardedSplit")}
+                                      "guardedSplit", "guardedInnerRetry")}
     for k in ("fov", "tan_fov", "apertureRadius", "userApertureRadius", "originShift", "apertureDistance",
               "focalLengthRatio"):
         out[k] = np.float32(getattr(c, k))

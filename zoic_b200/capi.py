@@ -42,7 +42,7 @@ class Constants(C.Structure):
         ("center", C.c_float * MAX_ELEMENTS),
         ("lutKey", C.c_float * LUT_SIZE), ("lutMinX", C.c_float * LUT_SIZE), ("lutMinY", C.c_float * LUT_SIZE),
         ("lutMaxX", C.c_float * LUT_SIZE), ("lutMaxY", C.c_float * LUT_SIZE),
-        ("guardedSplit", C.c_int32),
+        ("guardedSplit", C.c_int32), ("guardedInnerRetry", C.c_int32),
     ]
 
 

@@ -327,8 +327,9 @@ void build_lut(LensState* L, zoicb_constants* C, LutTraceFn fn, void* user) {
 // stopped early (rear rim, stop) do not idle through the rest of the stack.  Where to cut depends on where
 // this camera's attempts die: trace a few thousand attempts on the host (exact arithmetic, samples spread over
 // the sensor), histogram the stopping surface and minimise a simple issue-slot model.
-int choose_split(const LensState& L, float sensor_w, float sensor_h) {
+int choose_split(const LensState& L, float sensor_w, float sensor_h, int* inner_retry) {
     const int n = L.count;
+    *inner_retry = 0;
     if (n < 2) return 1;
     std::vector<double> stop_at(n, 0.0);
     double pass = 0.0, total = 0.0;
@@ -362,6 +363,10 @@ int choose_split(const LensState& L, float sensor_w, float sensor_h) {
         const double cost = (setup + k * per_surface) + survive_a * (n - k) * per_surface / util_b + 40.0;
         if (cost < best_cost) { best_cost = cost; best = k; }
     }
+    // in-pass re-sampling pays when, on average, at least half a warp is stopped inside stage A
+    double dead_a = 0.0;
+    for (int i = 0; i < best; ++i) dead_a += stop_at[i];
+    *inner_retry = dead_a / total > 0.5 ? 1 : 0;
     return best;
 }
 
@@ -517,8 +522,9 @@ zoicb_status build_camera(const zoicb_params& p, const float* rgb, int w, int h,
         C.aperture[i] = rows[i].aperture; C.center[i] = rows[i].center;
     }
     if (p.kolbSamplingLUT) build_lut(&L, &C, lut_fn, lut_user);  // :1691-1692
-    L.split = choose_split(L, p.sensorWidth, p.sensorHeight);
+    L.split = choose_split(L, p.sensorWidth, p.sensorHeight, &L.inner_retry);
     C.guardedSplit = L.split;
+    C.guardedInnerRetry = L.inner_retry;
     return ZOICB_OK;
 }
 

@@ -1,0 +1,257 @@
+// kernel_common.cuh -- device helpers shared by the kernel translation units: image-based aperture sampling,
+// per-block counter reduction, the EXACT per-sample functions, fast-math primitives.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "kernels.h"
+#include "lens_math.cuh"
+
+namespace zoicb {
+
+constexpr int kChunk = 2048;   // samples handed to a warp per grab of the global cursor (multiple of 32)
+
+// ------------------------------------------------------------------------------------------------
+// image-based aperture sampling (reference imageData::bokehSample, src/zoic.cpp:420-485)
+// ------------------------------------------------------------------------------------------------
+// std::upper_bound over a[0..n): first index whose value is greater than u, with libstdc++'s probe sequence
+// (first/len halving).  The loop runs a warp-uniform number of rounds (bit length of n) with predicated
+// updates instead of a per-lane trip count: no divergence, and -- the reason it is written this way -- no
+// lane leaves the loop early.  (With a data-dependent trip count ptxas 12.9 let the early lanes run ahead and
+// re-use the uniform registers that hold the table pointers while the late lanes were still reading them.)
+template <typename Load>
+__device__ __forceinline__ int upper_bound_rounds(int n, float u, Load load) {
+    int first = 0, len = n;
+    const int rounds = 32 - __clz(n);  // len halves every round: n -> 0 in at most bit_length(n) rounds
+    for (int it = 0; it < rounds; ++it) {
+        const int half = len >> 1;
+        const int mid = first + half;
+        const float v = load(mid < n ? mid : n - 1);
+        const bool live = len > 0;
+        const bool left = u < v;
+        first = (live && !left) ? mid + 1 : first;
+        len = live ? (left ? half : len - half - 1) : 0;
+    }
+    return first;
+}
+
+// The row tables (cdfRow, rowIndices: 8 bytes per image row) are always staged in dynamic shared memory --
+// s_rows[0..h) holds the CDF, s_rows[h..2h) the row indices -- and addressed as shared memory (no generic
+// pointers); the per-row column tables stay in global memory (L1/L2 resident).
+extern __shared__ float s_rows[];
+
+struct BokehView {
+    const float* cdf_col;     // global
+    const uint16_t* rel_col;
+    int w, h;
+};
+
+__device__ __forceinline__ void bokeh_sample(const BokehView& b, float u_row, float u_col, float* dx, float* dy) {
+    int r = upper_bound_rounds(b.h, u_row, [&](int i) { return s_rows[i]; });
+    if (r >= b.h) r = b.h - 1;
+    const int row = __float_as_int(s_rows[b.h + r]);
+    const int rrow = row - ((b.w - 1) / 2);  // centred with the WIDTH (:441)
+    const int start = row * b.w;
+    const float* __restrict__ col = b.cdf_col + start;
+    int c = upper_bound_rounds(b.w, u_col, [&](int i) { return __ldg(col + i); });
+    if (c >= b.w) c = b.w - 1;
+    const int rel = (int)__ldg(b.rel_col + start + c);
+    const int rcol = rel - ((b.h - 1) / 2);  // centred with the HEIGHT (:466)
+    const float fr = (float)rcol;
+    const float fc = xmul((float)rrow, -1.0f);
+    *dx = xmul(xdiv(fr, (float)b.w), 2.0f);
+    *dy = xmul(xdiv(fc, (float)b.h), 2.0f);
+}
+
+template <bool kImage>
+__device__ __forceinline__ void lens_sample(const BokehView& b, float u, float v, float* lx, float* ly) {
+    if (kImage) bokeh_sample(b, u, v, lx, ly);
+    else concentric_disk(u, v, lx, ly);
+}
+
+// two draws of the per-sample stream; the FIRST draw feeds the SECOND parameter (g++ evaluates the
+// reference's argument lists right to left; pinned in tests/test_oracle_port_vs_ref.py)
+__device__ __forceinline__ void draw_pair(Xor128& rng, float* first_param, float* second_param) {
+    uint32_t k1 = xor128_next(rng);
+    uint32_t k2 = xor128_next(rng);
+    *second_param = u32_to_unit(k1);
+    *first_param = u32_to_unit(k2);
+}
+
+__device__ __forceinline__ BokehView stage_bokeh(const CameraState& cam) {
+    BokehView b;
+    b.w = cam.bokeh.w; b.h = cam.bokeh.h;
+    b.cdf_col = cam.bokeh.cdf_column;
+    b.rel_col = cam.bokeh.rel_column;
+    for (int i = threadIdx.x; i < b.h; i += blockDim.x) {
+        s_rows[i] = cam.bokeh.cdf_row[i];
+        s_rows[b.h + i] = __int_as_float(cam.bokeh.row_indices[i]);
+    }
+    __syncthreads();
+    return b;
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-block counter reduction: warp shuffle -> shared -> one atomicAdd per counter per block
+// ------------------------------------------------------------------------------------------------
+struct LocalStats { unsigned rays, success, vignetted, tir, attempts, visits, reruns; };
+
+__device__ __forceinline__ void flush_stats(const LocalStats& ls, DeviceStats* g) {
+    __shared__ unsigned long long s_acc[7];
+    if (threadIdx.x < 7) s_acc[threadIdx.x] = 0ull;
+    __syncthreads();
+    unsigned v[7] = {ls.rays, ls.success, ls.vignetted, ls.tir, ls.attempts, ls.visits, ls.reruns};
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
+        unsigned s = __reduce_add_sync(0xffffffffu, v[k]);
+        if ((threadIdx.x & 31) == 0 && s) atomicAdd(&s_acc[k], (unsigned long long)s);
+    }
+    __syncthreads();
+    if (threadIdx.x < 7 && s_acc[threadIdx.x]) {
+        unsigned long long* dst = &g->rays + threadIdx.x;
+        atomicAdd(dst, s_acc[threadIdx.x]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// EXACT thin lens, one sample (src/zoic.cpp:1771-1848, :1297-1305)
+// ------------------------------------------------------------------------------------------------
+template <bool kImage>
+__device__ __forceinline__ void thin_exact_sample(const CameraState& cam, const BokehView& bk, float4 s, uint64_t gidx,
+                                                  uint64_t seed, float4* o4, float4* d4, LocalStats& ls) {
+    const ThinState& T = cam.thin;
+    Vec3 p = vmake(xmul(s.x, T.tan_fov), xmul(s.y, T.tan_fov), 1.0f);
+    const Vec3 dir0 = vnormalize(p);  // p - origin0 with origin0 = 0
+    Vec3 origin = vmake(0.0f, 0.0f, 0.0f);
+    Vec3 dir = dir0;
+    int tries = 0;
+    float weight = 1.0f;
+    ls.rays++;
+    ls.attempts++;
+    if (T.use_dof) {
+        float lx, ly;
+        lens_sample<kImage>(bk, s.z, s.w, &lx, &ly);
+        const float inter = fabsf(xdiv(T.focal_distance, dir0.z));
+        const Vec3 focus = vscale(dir0, inter);
+        origin = vmake(xmul(lx, T.aperture_radius), xmul(ly, T.aperture_radius), 0.0f);
+        dir = vnormalize(vsub(focus, origin));
+        if (T.use_ov) {
+            Xor128 rng = sample_stream(seed, gidx);
+            while (tries <= kMaxTries) {
+                // empericalOpticalVignetting
+                float qx = xsub(xmul(dir.x, T.ov_distance), origin.x);
+                float qy = xsub(xmul(dir.y, T.ov_distance), origin.y);
+                float hyp = xsqrt(xadd(xmul(qx, qx), xmul(qy, qy)));
+                if (fabsf(hyp) < T.ov_radius_true) break;
+                float u, v;
+                draw_pair(rng, &u, &v);
+                lens_sample<kImage>(bk, u, v, &lx, &ly);
+                origin = vmake(xmul(lx, T.aperture_radius), xmul(ly, T.aperture_radius), 0.0f);
+                dir = vnormalize(vsub(focus, origin));
+                ++tries;
+                ls.attempts++;
+            }
+        }
+        if (tries > kMaxTries) { weight = 0.0f; ls.vignetted++; }
+        else ls.success++;
+    }
+    dir.z = -dir.z;
+    weight = xmul(weight, cam.weight_scale);
+    *o4 = make_float4(origin.x, origin.y, origin.z, weight);
+    *d4 = make_float4(dir.x, dir.y, dir.z, (float)tries);
+}
+
+// ------------------------------------------------------------------------------------------------
+// EXACT raytraced lens, one sample (src/zoic.cpp:1850-1964, :1099-1158)
+// ------------------------------------------------------------------------------------------------
+template <bool kImage, bool kLut>
+__device__ __forceinline__ void kolb_exact_sample(const CameraState& cam, const BokehView& bk, float4 s, uint64_t gidx,
+                                                  uint64_t seed, float4* o4, float4* d4, LocalStats& ls) {
+    const LensState& L = cam.lens;
+    const KolbSampleState k = kolb_sample_setup<kLut, true>(L, s.x, s.y);
+    float lx, ly;
+    lens_sample<kImage>(bk, s.z, s.w, &lx, &ly);
+    Ray r;
+    r.o = vmake(k.fx, k.fy, L.origin_shift);
+    r.d = kolb_aim<kLut>(L, k, lx, ly, false);
+    int tries = 0;
+    Xor128 rng = sample_stream(seed, gidx);
+    ls.rays++;
+    for (;;) {
+        int visited;
+        const int rc = exact_march(L, r, &visited);
+        ls.attempts++;
+        ls.visits += visited;
+        if (rc == kTir) ls.tir++;
+        if (rc == kPass || tries > kMaxTries) break;
+        float u, v;
+        draw_pair(rng, &u, &v);
+        lens_sample<kImage>(bk, u, v, &lx, &ly);
+        r.o = vmake(k.fx, k.fy, L.origin_shift);
+        r.d = kolb_aim<kLut>(L, k, lx, ly, true);
+        ++tries;
+    }
+    float weight = 1.0f;
+    if (tries > kMaxTries) { weight = 0.0f; ls.vignetted++; }
+    else ls.success++;
+    weight = xmul(weight, cam.weight_scale);
+    // flip to look down -Z (:1960-1961)
+    *o4 = make_float4(-r.o.x, -r.o.y, -r.o.z, weight);
+    *d4 = make_float4(-r.d.x, -r.d.y, -r.d.z, (float)tries);
+}
+
+// ------------------------------------------------------------------------------------------------
+// fast-math primitives of the guarded path
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float approx_sqrt(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float approx_rcp(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float approx_rsqrt(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+
+enum { kUndecided = 3 };
+
+// approximate-division variant of the concentric map (same branch decisions: a, b are computed exactly)
+__device__ __forceinline__ void concentric_disk_fast(float ox, float oy, float* lx, float* ly) {
+    const float a = two_x_minus_one(ox);
+    const float b = two_x_minus_one(oy);
+    const bool first = xmul(a, a) > xmul(b, b);
+    const float num = first ? b : a, den = first ? a : b;
+    const float qt = num * approx_rcp(den);
+    const float r = first ? a : b;
+    const float phi = first ? 0.78539816339f * qt : 1.57079632679489661923f - 0.78539816339f * qt;
+    // phi in [-pi/4, 3pi/4]: phi + pi < 2pi always; (phi + pi/2) + pi may pass 2pi once
+    const float two_pi = ZOICB_PI_F * 2.0f;
+    const float xs = xsub(xadd(phi, ZOICB_PI_F), ZOICB_PI_F);
+    float vc = xadd(xadd(phi, ZOICB_PI_F * 0.5f), ZOICB_PI_F);
+    vc = vc >= two_pi ? xsub(vc, two_pi) : vc;
+    const float xc = xsub(vc, ZOICB_PI_F);
+    *lx = r * parabola_sin(xc);
+    *ly = r * parabola_sin(xs);
+}
+
+template <bool kImage>
+__device__ __forceinline__ void lens_sample_fast(const BokehView& b, float u, float v, float* lx, float* ly) {
+    if (kImage) bokeh_sample(b, u, v, lx, ly);
+    else concentric_disk_fast(u, v, lx, ly);
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// launch helpers
+// ------------------------------------------------------------------------------------------------
+inline int sm_count() {
+    static int count = 0;
+    if (!count) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&count, cudaDevAttrMultiProcessorCount, dev);
+        if (count <= 0) count = 148;
+    }
+    return count;
+}
+
+// kolb_pool.cu
+cudaError_t launch_kolb_pool(const CameraState& cam, const float4* samples, uint64_t n, uint64_t first_index, uint64_t seed,
+                             float4* origin_w, float4* dir_tries, DeviceStats* stats, cudaStream_t st, const Workspace& ws,
+                             size_t rows_smem, int* launches);
+
+}  // namespace zoicb
