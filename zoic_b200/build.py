@@ -51,7 +51,7 @@ def build_library(force=False, verbose=False):
         "-O3", "-std=c++17", "-lineinfo", "-Xptxas", "-v" if verbose else "-warn-spills",
         "-Xcompiler", "-fPIC,-ffp-contract=off,-fvisibility=hidden",
         "-I", os.path.join(ROOT, "include"), "-I", os.path.join(ROOT, "include", "arnold_shim"),
-    ]
+    ] + os.environ.get("ZOICB_NVCC_FLAGS", "").split()
     objs = []
     procs = []
     for s in srcs:

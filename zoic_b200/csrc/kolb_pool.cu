@@ -14,7 +14,13 @@ namespace zoicb {
 // many attempts die at the rear rim or at the stop.
 // ------------------------------------------------------------------------------------------------
 constexpr int kPoolSlots = 96;   // 3 x 32: one of the three stacks always holds a full pass (pigeonhole)
-constexpr int kWarpsPerCta = 8;
+#ifndef ZOICB_POOL_WARPS
+#define ZOICB_POOL_WARPS 7
+#endif
+constexpr int kWarpsPerCta = ZOICB_POOL_WARPS;
+#ifndef ZOICB_POOL_CTAS
+#define ZOICB_POOL_CTAS 4
+#endif
 
 struct alignas(16) WarpPool {
     float4 film[kPoolSlots];   // fx, fy, max_scale, translation
@@ -82,7 +88,7 @@ __device__ __forceinline__ int fast_march_range(const LensState& L, float gscale
 }
 
 template <int kN, bool kImage, bool kLut, bool kInner>
-__global__ void __launch_bounds__(kWarpsPerCta * 32, 3)
+__global__ void __launch_bounds__(kWarpsPerCta * 32, ZOICB_POOL_CTAS)
 kolb_pool_kernel(const __grid_constant__ CameraState cam, const float4* __restrict__ samples, uint32_t n,
                  uint64_t first_index, uint64_t seed, float4* __restrict__ origin_w, float4* __restrict__ dir_tries,
                  DeviceStats* stats, unsigned long long* chunk_counter, unsigned long long* queue,
@@ -285,7 +291,7 @@ template <bool kImage, bool kLut>
 static cudaError_t launch_pool_variant(const CameraState& cam, const float4* samples, uint64_t n, uint64_t first_index,
                                        uint64_t seed, float4* origin_w, float4* dir_tries, DeviceStats* stats, cudaStream_t st,
                                        const Workspace& ws, size_t rows_smem, int* launches) {
-    const unsigned grid = (unsigned)sm_count() * 3;  // persistent: 3 CTAs of 8 warps per SM
+    const unsigned grid = (unsigned)sm_count() * ZOICB_POOL_CTAS;  // persistent: ZOICB_POOL_CTAS CTAs of 8 warps per SM
     const int threads = kWarpsPerCta * 32;
     const size_t pool_smem = ((rows_smem + 15) & ~(size_t)15) + kWarpsPerCta * sizeof(WarpPool);
     // 32-bit sample offsets inside a launch, so very large batches go in slices
