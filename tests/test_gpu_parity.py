@@ -279,3 +279,64 @@ def test_guarded_kolb_bokeh_image_sizes(port, size):
                         useImage=1), port, n=60_000, image=img)
     _check_exact(dict(lensModel=0, focalLength=3.5, fStop=2.8, opticalVignettingDistance=2.0, useImage=1), port,
                  n=60_000, image=img)
+
+
+# ---------------------------------------------------------------------------------------------------
+# edge cases the reference leaves undefined or accidental
+# ---------------------------------------------------------------------------------------------------
+def test_edge_samples_follow_the_rulings(port):
+    from zoic_b200 import ZoicCamera, MODE_EXACT, MODE_GUARDED
+    from zoic_b200.workloads import lens_path
+    kw = dict(lensModel=1, lensDataPath=lens_path("double_gauss_f2.0.dat"), focalLength=5.0, fStop=2.0)
+    s = random_samples(20_000, seed=77)
+    s[0] = [0.0, 0.0, 0.3, 0.7]            # film centre: LUT entry 0, no interpolation (the reference steps before begin())
+    s[1] = [0.25, -0.1, 0.5, 0.5]          # lens square centre: 0/0 in the concentric map -> NaN ray, weight 1 (kept)
+    s[2] = [0.125 / 1.8, 0.0, 0.2, 0.9]    # film radius exactly on a LUT key
+    s[3] = [1.0, 2.0 / 3.0, 0.0, 0.0]      # corners of both squares
+    s[4] = [-1.0, -2.0 / 3.0, 1.0, 1.0]    # lens sample exactly 1.0 (a retry draw can round up to it)
+    ref = port.PortCamera(**kw)
+    o2, d2, _ = ref.generate(s, seed=5, first_index=0)
+    assert np.isnan(o2[1, :3]).all() and o2[1, 3] == 1.0 and d2[1, 3] == 0.0
+    for mode in (MODE_EXACT, MODE_GUARDED):
+        cam = ZoicCamera(mode=mode, **kw)
+        o, d, _ = _run_gpu(cam, s, seed=5, first_index=0)
+        assert np.isnan(o[1, :3]).all() and o[1, 3] == 1.0 and d[1, 3] == 0.0
+        keep = np.ones(len(s), bool)
+        keep[1] = False
+        if mode == MODE_EXACT:
+            assert bits_equal(o[keep], o2[keep]) and bits_equal(d[keep], d2[keep])
+        else:
+            res = compare_rays(o[keep], d[keep], o2[keep], d2[keep])
+            assert res["path_flips"] == 0 and res["out_of_tol"] == 0, res
+        cam.close()
+    ref.close()
+
+
+def test_film_radius_beyond_the_lut_clamps(port):
+    """sensorWidth 9 cm puts film points beyond the last LUT key (3.875 cm): last entry, extrapolated (ruling)."""
+    from zoic_b200.workloads import lens_path
+    _check_exact(dict(lensModel=1, lensDataPath=lens_path("double_gauss_f2.0.dat"), focalLength=5.0, fStop=2.0,
+                      sensorWidth=9.0, sensorHeight=6.0), port, n=40_000)
+    _check_guarded(dict(lensModel=1, lensDataPath=lens_path("double_gauss_f2.0.dat"), focalLength=5.0, fStop=2.0,
+                        sensorWidth=9.0, sensorHeight=6.0), port, n=100_000)
+
+
+def test_large_batch_spans_many_chunks_and_keeps_counters(port):
+    """2^22 samples through the persistent kernels: every sample written exactly once, counters add up."""
+    from zoic_b200 import ZoicCamera
+    from zoic_b200.workloads import config4
+    wl = config4()
+    cam = ZoicCamera(**wl.params)
+    n = 1 << 22
+    s = cam.synth_samples(wl.W, wl.H, wl.spp, wl.seed, 0, n)
+    o = torch.full((n, 4), float("nan"), device="cuda")
+    d = torch.full((n, 4), float("nan"), device="cuda")
+    cam.reset_stats()
+    cam.create_rays(s, seed=wl.seed, first_index=0, out=(o, d))
+    torch.cuda.synchronize()
+    st = cam.stats()
+    assert not torch.isnan(o[:, 3]).any() and not torch.isnan(d[:, 3]).any()
+    assert st["rays"] == n and st["success"] + st["vignetted"] == n
+    assert st["success"] == int((o[:, 3] != 0).sum()) and st["vignetted"] == int((o[:, 3] == 0).sum())
+    assert st["attempts"] == n + int(d[:, 3].sum())
+    cam.close()
