@@ -167,6 +167,7 @@ def main():
     ap.add_argument("--samples", type=int, default=0, help="override samples per GPU per step (debug)")
     ap.add_argument("--e2e-samples", type=int, default=1 << 26)
     ap.add_argument("--cpu-samples", type=int, default=1 << 22, help="CPU baseline sample size (all cores)")
+    ap.add_argument("--gather", action="store_true", help="N > 1: also time generation + NCCL all-gather of a 2^26-ray tile")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -258,10 +259,20 @@ def main():
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     hbm_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
+    # DRAM traffic per launch: dram__bytes_read.sum + dram__bytes_write.sum of the same kernel from the committed
+    # ncu capture (profiles/), scaled from the captured launch size to this launch (bytes per ray are size-independent)
+    traffic = None
+    try:
+        cap = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        key = "kolb" if model == 1 else "thin"
+        if key in cap:
+            traffic = cap[key]["dram_bytes_per_ray"] * n
+    except Exception:
+        pass
     if model == 1:
         fp32_peak = zcam.measure_fp32_peak(local)
         roofline = {"bound": "fp32", "achieved": flops / kernel_s / 1e12, "peak": fp32_peak, "unit": "TFLOP/s",
-                    "frac": flops / kernel_s / 1e12 / fp32_peak, "traffic": None,
+                    "frac": flops / kernel_s / 1e12 / fp32_peak, "traffic": traffic,
                     "peak_source": "FFMA throughput measured live by zoicb_measure_fp32_peak (nominal 74.4 TFLOP/s at 1965 MHz)",
                     "flops_per_ray": flops / n, "attempts_per_ray": stats["attempts"] / max(1, stats["rays"]),
                     "element_visits_per_ray": stats["element_visits"] / max(1, stats["rays"]),
@@ -269,7 +280,7 @@ def main():
                             "peak_source": hbm_src, "bytes_per_ray": 48}}
     else:
         roofline = {"bound": "hbm", "achieved": hbm_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_gbs / hbm_peak,
-                    "traffic": None, "peak_source": hbm_src, "bytes_per_ray": 48,
+                    "traffic": traffic, "peak_source": hbm_src, "bytes_per_ray": 48,
                     "attempts_per_ray": stats["attempts"] / max(1, stats["rays"])}
 
     # end to end through the host-buffer entry point: pinned host memory in, pinned host memory out
@@ -296,6 +307,26 @@ def main():
                "api": "zoicb_generate_host (pinned host buffers, 3-slot copy/compute pipeline)"}
         del hs, ho, hd
 
+    # optional: generation + final gather of the ray buffer over NVLink (north_star's "final NCCL gather"), on a tile
+    gather = None
+    if world > 1 and args.gather:
+        from zoic_b200.distributed import gather_rays
+        m = min(1 << 26, n)
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        gather_rays(origin_w[:m], dir_tries[:m])  # warm-up
+        barrier()
+        g0.record()
+        reps = 3
+        for _ in range(reps):
+            cam.create_rays(samples[:m], seed=wl.seed, first_index=first, out=(origin_w[:m], dir_tries[:m]))
+            gather_rays(origin_w[:m], dir_tries[:m])
+        g1.record()
+        barrier()
+        tg = torch.tensor([g0.elapsed_time(g1) / reps], dtype=torch.float64, device=dev)
+        dist.all_reduce(tg, op=dist.ReduceOp.MAX)
+        gather = {"value": world * m / (float(tg.item()) * 1e-3) / 1e6, "unit": UNIT, "rays_per_rank": m,
+                  "what": "generate + all-gather of both float4 ray buffers to every rank (NCCL), max over ranks"}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cpu = cpu_reference_rate(wl, args.cpu_samples)
@@ -304,13 +335,16 @@ def main():
     if rank == 0:
         cfg = wl.describe()
         cfg.update({"samples_per_gpu_per_step": n, "arithmetic_mode": mode_name,
-                    "l2": "inputs (%.1f GB per step) are larger than L2; no flush needed" % (16.0 * n / 1e9),
+                    "l2": ("inputs (%.1f GB per step) are larger than L2; no flush needed" % (16.0 * n / 1e9)) if 16.0 * n > 2.6e8
+                          else "batch (%.0f MB in + out) fits in L2: the number is L2-assisted" % (48.0 * n / 1e6),
                     "sharding": "rank r owns samples [r*n,(r+1)*n) of the %dx%dx%d grid" % (wl.W, wl.H, wl.spp * world)})
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg, "clocks": clocks,
                 "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
                 "stats": stats}
+        if gather:
+            line["gather"] = gather
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

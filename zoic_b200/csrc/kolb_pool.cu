@@ -202,6 +202,7 @@ kolb_pool_kernel(const __grid_constant__ CameraState cam, const float4* __restri
             const bool act = (int)lane < m;
             const int slot = act ? P.qb[nB - 1 - lane] : 0;
             nB -= m;
+            __syncwarp();   // pops are complete before this pass pushes onto the same stack positions
             float4 r0 = make_float4(0, 0, 0, 0), r1 = make_float4(0, 0, 1, 0);
             if (act) { r0 = P.ray0[slot]; r1 = P.ray1[slot]; }
             float ox = r0.x, oy = r0.y, oz = r0.z, ux = r0.w, uy = r1.x, uz = r1.y;
@@ -227,6 +228,7 @@ kolb_pool_kernel(const __grid_constant__ CameraState cam, const float4* __restri
             const bool act = (int)lane < m;
             const int slot = act ? P.qa[nA - 1 - lane] : 0;
             nA -= m;
+            __syncwarp();   // pops are complete before this pass pushes onto the same stack positions
             float4 f = make_float4(0, 0, 1, 0), rt = make_float4(0, 1, 0.5f, 0.25f), r1 = make_float4(0, 0, 0, 0);
             uint4 g4 = make_uint4(1, 2, 3, 4);
             if (act) { f = P.film[slot]; rt = P.rot[slot]; g4 = P.rng[slot]; r1 = P.ray1[slot]; }
