@@ -103,7 +103,7 @@ cudaError_t get_workspace(zoicb_ctx* c, cudaStream_t st, uint64_t n, Workspace* 
     if (want > (1ull << 27)) want = 1ull << 27;
     cudaError_t e;
     if (!w.counters) {
-        if ((e = cudaMalloc(&w.counters, 2 * sizeof(unsigned long long))) != cudaSuccess) return e;
+        if ((e = cudaMalloc(&w.counters, 4 * sizeof(unsigned long long))) != cudaSuccess) return e;
     }
     if (w.capacity < want) {
         if (w.queue) {
@@ -243,7 +243,7 @@ zoicb_status zoicb_generate(zoicb_ctx* ctx, const void* d_samples, uint64_t n, u
     ZCUDA(cudaSetDevice(ctx->device), "cudaSetDevice");
     int launches = 0;
     Workspace ws = {nullptr, nullptr, 0};
-    if (ctx->mode == ZOICB_MODE_GUARDED) ZCUDA(get_workspace(ctx, (cudaStream_t)stream, n, &ws), "workspace");
+    ZCUDA(get_workspace(ctx, (cudaStream_t)stream, n, &ws), "workspace");
     cudaError_t e = launch_generate(ctx->host.state, ctx->mode, (const float4*)d_samples, n, first_index, rng_seed,
                                     (float4*)d_origin_w, (float4*)d_dir_tries, ctx->d_stats, (cudaStream_t)stream, ws, &launches);
     count_launches(launches);
@@ -298,7 +298,7 @@ zoicb_status zoicb_generate_host(zoicb_ctx* ctx, const float* h_samples, uint64_
         if (!direct) { std::memcpy(ctx->h_in[s], src, m * sizeof(float4)); src = (const float*)ctx->h_in[s]; }
         ZCUDA(cudaMemcpyAsync(ctx->d_in[s], src, m * sizeof(float4), cudaMemcpyHostToDevice, ctx->streams[s]), "H2D");
         Workspace ws = {nullptr, nullptr, 0};
-        if (ctx->mode == ZOICB_MODE_GUARDED) ZCUDA(get_workspace(ctx, ctx->streams[s], m, &ws), "workspace");
+        ZCUDA(get_workspace(ctx, ctx->streams[s], m, &ws), "workspace");
         cudaError_t e = launch_generate(ctx->host.state, ctx->mode, ctx->d_in[s], m, first_index + b, rng_seed, ctx->d_o[s],
                                         ctx->d_d[s], ctx->d_stats, ctx->streams[s], ws, &launches);
         if (e != cudaSuccess) { count_launches(launches); return cuda_fail(e, "zoicb_generate_host launch"); }

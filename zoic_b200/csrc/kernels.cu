@@ -37,29 +37,92 @@ exact_kernel(const __grid_constant__ CameraState cam, const float4* __restrict__
     flush_stats(ls, stats);
 }
 
-// Re-run of the samples the guarded kernels could not decide: one thread per queued sample index.
-template <int kModel, bool kImage, bool kLut>
-__global__ void __launch_bounds__(256)
-rerun_kernel(const __grid_constant__ CameraState cam, const float4* __restrict__ samples, uint64_t first_index,
-             uint64_t seed, float4* __restrict__ origin_w, float4* __restrict__ dir_tries, DeviceStats* stats,
-             int stage_rows, const unsigned long long* __restrict__ queue, const unsigned long long* __restrict__ count,
-             unsigned long long capacity) {
+// ------------------------------------------------------------------------------------------------
+// EXACT raytraced lens on the persistent-warp / per-lane regeneration schedule.  Same arithmetic and same
+// results as kolb_exact_sample (bit-identical); a lane that finishes its sample takes the next work item at
+// once instead of idling until the slowest sample of its warp has used up its retries.  Work items are either
+// the samples [0, m) themselves or the entries of the undecided-sample queue of the guarded kernel.
+// ------------------------------------------------------------------------------------------------
+template <bool kImage, bool kLut, bool kQueued>
+__global__ void __launch_bounds__(256, 3)
+kolb_exact_persistent_kernel(const __grid_constant__ CameraState cam, const float4* __restrict__ samples, uint64_t m_direct,
+                             uint64_t first_index, uint64_t seed, float4* __restrict__ origin_w,
+                             float4* __restrict__ dir_tries, DeviceStats* stats, unsigned long long* cursor,
+                             const unsigned long long* __restrict__ queue, const unsigned long long* __restrict__ queue_count,
+                             unsigned long long capacity) {
     BokehView bk;
     if (kImage) bk = stage_bokeh(cam);
-    (void)stage_rows;
+    const LensState& L = cam.lens;
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
     LocalStats ls = {0, 0, 0, 0, 0, 0, 0};
-    unsigned long long m = *count;
-    if (m > capacity) m = capacity;
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < m; q += stride) {
-        const uint64_t i = queue[q];
-        const float4 s = samples[i];
-        float4 o4, d4;
-        if (kModel == 0) thin_exact_sample<kImage>(cam, bk, s, first_index + i, seed, &o4, &d4, ls);
-        else kolb_exact_sample<kImage, kLut>(cam, bk, s, first_index + i, seed, &o4, &d4, ls);
-        origin_w[i] = o4;
-        dir_tries[i] = d4;
-        ls.reruns++;
+    unsigned long long m = m_direct;
+    if (kQueued) { m = *queue_count; if (m > capacity) m = capacity; }
+    constexpr unsigned kGrab = 256;   // work items per grab of the global cursor
+    uint64_t cur = 0, end = 0;
+    bool exhausted = false, have = false, fresh = false;
+    uint64_t idx = 0;
+    KolbSampleState k;
+    k.fx = k.fy = k.max_scale = k.translation = k.sn = 0.0f; k.cs = 1.0f;
+    Xor128 rng = {0, 0, 0, 0};
+    int tries = 0;
+    float ua = 0.0f, ub = 0.0f;
+    for (;;) {
+        const unsigned need = __ballot_sync(0xffffffffu, !have);
+        if (need) {
+            if (cur == end && !exhausted) {
+                unsigned long long base = 0;
+                if (lane == 0) base = atomicAdd(cursor, (unsigned long long)kGrab);
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (base >= m) { exhausted = true; }
+                else { cur = base; end = (base + kGrab < m) ? base + kGrab : m; }
+            }
+            const unsigned avail = (unsigned)(end - cur);
+            const unsigned want = __popc(need);
+            const unsigned take = want < avail ? want : avail;
+            const unsigned rank = __popc(need & lt_mask);
+            if (!have && rank < take) {
+                idx = kQueued ? queue[cur + rank] : cur + rank;
+                const float4 s = samples[idx];
+                k = kolb_sample_setup<kLut, true>(L, s.x, s.y);
+                rng = sample_stream(seed, first_index + idx);
+                ua = s.z;
+                ub = s.w;
+                tries = 0;
+                have = true;
+                fresh = true;
+                ls.rays++;
+                if (kQueued) ls.reruns++;
+            }
+            cur += take;
+        }
+        if (!__any_sync(0xffffffffu, have)) {
+            if (exhausted) break;
+            continue;
+        }
+        if (have) {
+            if (!fresh) { draw_pair(rng, &ua, &ub); ++tries; }
+            float lx, ly;
+            lens_sample<kImage>(bk, ua, ub, &lx, &ly);
+            Ray r;
+            r.o = vmake(k.fx, k.fy, L.origin_shift);
+            r.d = kolb_aim<kLut>(L, k, lx, ly, !fresh);
+            fresh = false;
+            int visited;
+            const int rc = exact_march(L, r, &visited);
+            ls.attempts++;
+            ls.visits += visited;
+            if (rc == kTir) ls.tir++;
+            if (rc == kPass || tries > kMaxTries) {
+                float weight = 1.0f;
+                if (tries > kMaxTries) { weight = 0.0f; ls.vignetted++; }
+                else ls.success++;
+                weight = xmul(weight, cam.weight_scale);
+                origin_w[idx] = make_float4(-r.o.x, -r.o.y, -r.o.z, weight);
+                dir_tries[idx] = make_float4(-r.d.x, -r.d.y, -r.d.z, (float)tries);
+                have = false;
+            }
+        }
     }
     flush_stats(ls, stats);
 }
@@ -233,17 +296,26 @@ static cudaError_t launch_variant(const CameraState& cam, int mode, const float4
                                   const Workspace& ws, size_t smem, int stage, int* launches) {
     const int threads = 256;
     if (mode == 1 && kModel == 1) {  // guarded fast path + exact re-run of the undecided samples
-        cudaError_t e = cudaMemsetAsync(ws.counters, 0, 2 * sizeof(unsigned long long), st);
+        cudaError_t e = cudaMemsetAsync(ws.counters, 0, 4 * sizeof(unsigned long long), st);
         if (e != cudaSuccess) return e;
         e = launch_kolb_pool(cam, samples, n, first_index, seed, origin_w, dir_tries, stats, st, ws, smem, launches);
         if (e != cudaSuccess) return e;
-        rerun_kernel<kModel, kImage, kLut><<<(unsigned)sm_count() * 2, threads, smem, st>>>(
-            cam, samples, first_index, seed, origin_w, dir_tries, stats, stage, ws.queue, ws.counters + 1, ws.capacity);
+        kolb_exact_persistent_kernel<kImage, kLut, true><<<(unsigned)sm_count() * 3, threads, smem, st>>>(
+            cam, samples, 0, first_index, seed, origin_w, dir_tries, stats, ws.counters + 2, ws.queue, ws.counters + 1,
+            ws.capacity);
+        if (launches) *launches += 1;
+        return cudaGetLastError();
+    }
+    if (kModel == 1 && ws.counters && n >= 65536) {  // EXACT mode on a big batch: same arithmetic, persistent schedule
+        cudaError_t e = cudaMemsetAsync(ws.counters, 0, 4 * sizeof(unsigned long long), st);
+        if (e != cudaSuccess) return e;
+        kolb_exact_persistent_kernel<kImage, kLut, false><<<(unsigned)sm_count() * 3, threads, smem, st>>>(
+            cam, samples, n, first_index, seed, origin_w, dir_tries, stats, ws.counters + 2, nullptr, nullptr, 0);
         if (launches) *launches += 1;
         return cudaGetLastError();
     }
     if (mode == 1 && kModel == 0 && cam.thin.use_dof && cam.thin.use_ov) {  // retry loop present: persistent schedule
-        cudaError_t e = cudaMemsetAsync(ws.counters, 0, 2 * sizeof(unsigned long long), st);
+        cudaError_t e = cudaMemsetAsync(ws.counters, 0, 4 * sizeof(unsigned long long), st);
         if (e != cudaSuccess) return e;
         thin_persistent_kernel<kImage><<<(unsigned)sm_count() * 4, threads, smem, st>>>(cam, samples, n, first_index, seed, origin_w,
                                                                                       dir_tries, stats, stage, ws.counters);

@@ -7,8 +7,9 @@
 
 namespace zoicb {
 
-// Per-stream scratch of the guarded mode: counters[0] = chunk cursor, counters[1] = number of queued
-// (undecided) sample indices, queue[capacity] = those indices.
+// Per-stream scratch: counters[0] = chunk cursor of the main kernel, counters[1] = number of queued (undecided)
+// sample indices, counters[2] = work cursor of the exact persistent kernel, counters[3] spare;
+// queue[capacity] = the undecided sample indices.
 struct Workspace {
     unsigned long long* counters;
     unsigned long long* queue;

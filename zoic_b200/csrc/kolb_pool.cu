@@ -129,8 +129,10 @@ kolb_pool_kernel(const __grid_constant__ CameraState cam, const float4* __restri
             if (tries > (unsigned)kMaxTries) { weight = 0.0f; ls.vignetted++; ux = 0.0f; uy = 0.0f; uz = 1.0f; }
             else ls.success++;
             weight *= cam.weight_scale;
-            __stcs(origin_w + idx, make_float4(-ox, -oy, -oz, weight));
-            __stcs(dir_tries + idx, make_float4(-ux, -uy, -uz, (float)tries));
+            // plain (write-back) stores: the two 16-byte halves of a 32-byte sector are written by different lanes at
+            // different times and must meet in L2; streaming stores get evicted half-written and cost a read-modify-write
+            origin_w[idx] = make_float4(-ox, -oy, -oz, weight);
+            dir_tries[idx] = make_float4(-ux, -uy, -uz, (float)tries);
             ls.rays++;
             ls.attempts += tries + 1;
             ls.visits += pk_visits(packed);
