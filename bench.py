@@ -210,12 +210,11 @@ def main():
     for b in range(0, n, tile):
         m = min(tile, n - b)
         cam.synth_samples(wl.W, wl.H, wl.spp * world, wl.seed, first + b, m, out=samples[b:b + m])
-    origin_w = torch.empty((n, 4), dtype=torch.float32, device=dev)
-    dir_tries = torch.empty((n, 4), dtype=torch.float32, device=dev)
+    rays = torch.empty((n, 8), dtype=torch.float32, device=dev)   # one 32-byte zoicb_ray per sample
     torch.cuda.synchronize()
 
     def step():
-        cam.create_rays(samples, seed=wl.seed, first_index=first, out=(origin_w, dir_tries))
+        cam.create_rays(samples, seed=wl.seed, first_index=first, out=rays)
 
     def barrier():
         if world > 1:
@@ -288,16 +287,15 @@ def main():
     if not args.no_e2e:
         m = min(args.e2e_samples, n)
         hs = torch.empty((m, 4), dtype=torch.float32).pin_memory()
-        ho = torch.empty((m, 4), dtype=torch.float32).pin_memory()
-        hd = torch.empty((m, 4), dtype=torch.float32).pin_memory()
+        hr = torch.empty((m, 8), dtype=torch.float32).pin_memory()
         hs.copy_(samples[:m])
         torch.cuda.synchronize()
-        cam.create_rays_host(hs, seed=wl.seed, first_index=first, out=(ho, hd))  # warm-up (allocates staging)
+        cam.create_rays_host(hs, seed=wl.seed, first_index=first, out=hr)  # warm-up (allocates staging)
         barrier()
         t0 = time.perf_counter()
         reps = 3
         for _ in range(reps):
-            cam.create_rays_host(hs, seed=wl.seed, first_index=first, out=(ho, hd))
+            cam.create_rays_host(hs, seed=wl.seed, first_index=first, out=hr)
         torch.cuda.synchronize()
         dt = torch.tensor([(time.perf_counter() - t0) / reps], dtype=torch.float64, device=dev)
         if world > 1:
@@ -305,7 +303,7 @@ def main():
         e2e = {"value": world * m / float(dt.item()) / 1e6, "unit": UNIT, "h2d_bytes_per_step": 16 * m,
                "d2h_bytes_per_step": 32 * m, "samples_per_step": m,
                "api": "zoicb_generate_host (pinned host buffers, 3-slot copy/compute pipeline)"}
-        del hs, ho, hd
+        del hs, hr
 
     # optional: generation + final gather of the ray buffer over NVLink (north_star's "final NCCL gather"), on a tile
     gather = None
@@ -313,19 +311,19 @@ def main():
         from zoic_b200.distributed import gather_rays
         m = min(1 << 26, n)
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        gather_rays(origin_w[:m], dir_tries[:m])  # warm-up
+        gather_rays(rays[:m])  # warm-up
         barrier()
         g0.record()
         reps = 3
         for _ in range(reps):
-            cam.create_rays(samples[:m], seed=wl.seed, first_index=first, out=(origin_w[:m], dir_tries[:m]))
-            gather_rays(origin_w[:m], dir_tries[:m])
+            cam.create_rays(samples[:m], seed=wl.seed, first_index=first, out=rays[:m])
+            gather_rays(rays[:m])
         g1.record()
         barrier()
         tg = torch.tensor([g0.elapsed_time(g1) / reps], dtype=torch.float64, device=dev)
         dist.all_reduce(tg, op=dist.ReduceOp.MAX)
         gather = {"value": world * m / (float(tg.item()) * 1e-3) / 1e6, "unit": UNIT, "rays_per_rank": m,
-                  "what": "generate + all-gather of both float4 ray buffers to every rank (NCCL), max over ranks"}
+                  "what": "generate + all-gather of the 32-byte ray records to every rank (NCCL), max over ranks"}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:

@@ -106,6 +106,19 @@ typedef struct zoicb_constants {
     int32_t guardedInnerRetry; /* 1: rays stopped in stage A re-sample inside the pass (high-rejection cameras) */
 } zoicb_constants;
 
+/* One generated camera ray: a 32-byte record (the fields of AtCameraOutput that zoic writes).
+ *   origin, dir : camera space, looking down -Z, cm
+ *   weight      : 0 when every retry was vignetted, else the exposure scale (reference :1951-1953, :1981-1987)
+ *   tries       : number of re-samples, as a float; tries > 0 <=> the reference also sets dOdy = origin,
+ *                 dDdy = dir (:1974-1977)
+ * Arrays of rays must be 32-byte aligned (each record is written with one 256-bit store). */
+typedef struct zoicb_ray {
+    float origin[3];
+    float weight;
+    float dir[3];
+    float tries;
+} zoicb_ray;
+
 typedef struct zoicb_ctx zoicb_ctx;
 
 ZOICB_API void zoicb_default_params(zoicb_params* p);
@@ -125,28 +138,28 @@ ZOICB_API int zoicb_get_mode(const zoicb_ctx* ctx);
  * how much head-room the shipped margins have).  Not meant to be called while generate calls are in flight. */
 ZOICB_API zoicb_status zoicb_set_guard_scale(zoicb_ctx* ctx, float scale);
 
-/* camera_create_ray for a flat batch.  All pointers are DEVICE pointers owned by the caller:
- *   d_samples    n x float4 (sx, sy, lensx, lensy)          -- AtCameraInput fields zoic reads
- *   d_origin_w   n x float4 (origin.x, origin.y, origin.z, weight)
- *   d_dir_tries  n x float4 (dir.x, dir.y, dir.z, (float)tries)   tries > 0 <=> the reference also sets
- *                                                            dOdy = origin, dDdy = dir (:1974-1977)
+/* camera_create_ray for a flat batch.  Both pointers are DEVICE pointers owned by the caller:
+ *   d_samples  n x float4 (sx, sy, lensx, lensy)   -- the AtCameraInput fields zoic reads
+ *   d_rays     n x zoicb_ray, 32-byte aligned
  * Initial AtCameraOutput state is origin = 0, weight = 1.  Retried samples draw from a per-sample
  * xorshift128 stream seeded from (rng_seed, first_index + i), so results do not
- * depend on batch boundaries, launch order or GPU count.  Asynchronous on `stream` (a cudaStream_t). */
+ * depend on batch boundaries, launch order or GPU count.  Asynchronous on `stream` (a cudaStream_t).
+ * In GUARDED mode a zero-weight ray carries the film point and the optical axis as origin / dir (the
+ * reference leaves the half-traced state of its last failed attempt there; EXACT mode reproduces that). */
 ZOICB_API zoicb_status zoicb_generate(zoicb_ctx* ctx, const void* d_samples, uint64_t n, uint64_t first_index,
-                            uint64_t rng_seed, void* d_origin_w, void* d_dir_tries, void* stream);
+                                      uint64_t rng_seed, zoicb_ray* d_rays, void* stream);
 
 /* The same with HOST buffers: pipelines host->device copies, kernels and device->host copies through
  * pinned staging chunks.  Synchronous. */
 ZOICB_API zoicb_status zoicb_generate_host(zoicb_ctx* ctx, const float* h_samples, uint64_t n, uint64_t first_index,
-                                 uint64_t rng_seed, float* h_origin_w, float* h_dir_tries);
+                                           uint64_t rng_seed, zoicb_ray* h_rays);
 
 /* camera_create_ray for ONE sample (the shape of Arnold's per-sample callback): sample = (sx, sy, lensx,
- * lensy), outputs origin_w[4], dir_tries[4] in host memory.  Uses per-thread pinned staging and a per-thread
+ * lensy), one zoicb_ray in host memory.  Uses per-thread pinned staging and a per-thread
  * stream, so it may be called concurrently from many render threads; it is a launch + two tiny copies per
  * call, i.e. a compatibility path -- throughput comes from the batched entry points above. */
 ZOICB_API zoicb_status zoicb_generate_one(zoicb_ctx* ctx, const float* sample, uint64_t sample_index,
-                                          uint64_t rng_seed, float* origin_w, float* dir_tries);
+                                          uint64_t rng_seed, zoicb_ray* ray);
 
 /* Synthetic camera samples for benchmarks and parity tests: sample index i is
  * pixel-major / spp-minor over a W x H image, four 24-bit uniforms from a counter hash of (seed, i). */

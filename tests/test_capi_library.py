@@ -40,14 +40,15 @@ def test_struct_layouts_match_the_header():
     src = r'''
     #include <stdio.h>
     #include "zoicb.h"
-    int main(void){ printf("%zu %zu %zu\n", sizeof(zoicb_params), sizeof(zoicb_stats), sizeof(zoicb_constants)); return 0; }
+    int main(void){ printf("%zu %zu %zu %zu\n", sizeof(zoicb_params), sizeof(zoicb_stats), sizeof(zoicb_constants), sizeof(zoicb_ray)); return 0; }
     '''
     import tempfile
     with tempfile.TemporaryDirectory() as d:
         open(os.path.join(d, "t.c"), "w").write(src)
         subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), os.path.join(d, "t.c"), "-o", os.path.join(d, "t")], check=True)
         sizes = [int(x) for x in subprocess.run([os.path.join(d, "t")], capture_output=True, text=True, check=True).stdout.split()]
-    assert sizes == [C.sizeof(capi.Params), C.sizeof(capi.Stats), C.sizeof(capi.Constants)]
+    assert sizes == [C.sizeof(capi.Params), C.sizeof(capi.Stats), C.sizeof(capi.Constants), C.sizeof(capi.Ray)]
+    assert C.sizeof(capi.Ray) == 32
 
 
 def test_defaults_are_the_reference_node_defaults():
@@ -77,7 +78,7 @@ def test_no_gpu_fails_loudly():
 def test_null_arguments_are_rejected():
     lib = capi.load()
     assert lib.zoicb_create(None, None, 0, 0, 0, 0, None) == capi.ERR_INVALID_ARGUMENT
-    assert lib.zoicb_generate(None, None, 1, 0, 0, None, None, None) == capi.ERR_INVALID_ARGUMENT
+    assert lib.zoicb_generate(None, None, 1, 0, 0, None, None) == capi.ERR_INVALID_ARGUMENT
     assert lib.zoicb_get_stats(None, None) == capi.ERR_INVALID_ARGUMENT
     assert b"null" in lib.zoicb_last_error()
     assert lib.zoicb_version().startswith(b"zoicb")

@@ -46,10 +46,10 @@ def _worker(rank, world, port_no, n, result_path):
     s = port.synth_samples(wl.W, wl.H, wl.spp, wl.seed, base + first, count)
     cam = port.PortCamera(**wl.params)
     o, d, st = cam.generate(s, seed=wl.seed, first_index=base + first)
-    go, gd = gather_rays(torch.from_numpy(o), torch.from_numpy(d))
+    g = gather_rays(torch.from_numpy(np.concatenate([o, d], axis=1)))
     total = reduce_stats(st, torch.device("cpu"))
     if rank == 0:
-        np.savez(result_path, o=go.numpy(), d=gd.numpy(), stats=np.array([total[k] for k in sorted(total)]))
+        np.savez(result_path, o=g.numpy()[:, :4], d=g.numpy()[:, 4:], stats=np.array([total[k] for k in sorted(total)]))
     dist.barrier()
     dist.destroy_process_group()
 

@@ -16,9 +16,10 @@ torch = pytest.importorskip("torch")
 def _run_gpu(cam, s, seed, first_index=0):
     t = torch.from_numpy(s).cuda()
     cam.reset_stats()
-    o, d = cam.create_rays(t, seed=seed, first_index=first_index)
+    rays = cam.create_rays(t, seed=seed, first_index=first_index)
     torch.cuda.synchronize()
-    return o.cpu().numpy(), d.cpu().numpy(), cam.stats()
+    r = rays.cpu().numpy()
+    return np.ascontiguousarray(r[:, :4]), np.ascontiguousarray(r[:, 4:]), cam.stats()
 
 
 def _check_exact(kw, port, n=200_000, seed=11, image=None):
@@ -123,13 +124,12 @@ def test_host_buffer_entry_point(port):
     ref = port.PortCamera(**kw)
     s = random_samples(300_000, seed=5)
     o2, d2, _ = ref.generate(s, seed=4, first_index=77, nthreads=8)
-    o, d = cam.create_rays_host(s, seed=4, first_index=77)             # pageable numpy memory
-    assert bits_equal(o, o2) and bits_equal(d, d2)
+    r = cam.create_rays_host(s, seed=4, first_index=77)                # pageable numpy memory
+    assert bits_equal(r[:, :4], o2) and bits_equal(r[:, 4:], d2)
     sp = torch.from_numpy(s).pin_memory()
-    op = torch.empty((len(s), 4), dtype=torch.float32).pin_memory()
-    dp = torch.empty((len(s), 4), dtype=torch.float32).pin_memory()
-    cam.create_rays_host(sp, seed=4, first_index=77, out=(op, dp))     # pinned memory, direct DMA
-    assert bits_equal(op.numpy(), o2) and bits_equal(dp.numpy(), d2)
+    rp = torch.empty((len(s), 8), dtype=torch.float32).pin_memory()
+    cam.create_rays_host(sp, seed=4, first_index=77, out=rp)           # pinned memory, direct DMA
+    assert bits_equal(rp.numpy()[:, :4], o2) and bits_equal(rp.numpy()[:, 4:], d2)
     cam.close()
     ref.close()
 
@@ -138,8 +138,8 @@ def test_empty_batch_and_errors():
     from zoic_b200 import ZoicCamera, capi
     cam = ZoicCamera(lensModel=0, focalLength=3.5, fStop=2.8)
     t = torch.empty((0, 4), dtype=torch.float32, device="cuda")
-    o, d = cam.create_rays(t)
-    assert o.shape == (0, 4)
+    r = cam.create_rays(t)
+    assert r.shape == (0, 8)
     cam.close()
     with pytest.raises(capi.ZoicError) as e:
         ZoicCamera(lensModel=1, lensDataPath="/nonexistent/lens.dat")
@@ -329,11 +329,11 @@ def test_large_batch_spans_many_chunks_and_keeps_counters(port):
     cam = ZoicCamera(**wl.params)
     n = 1 << 22
     s = cam.synth_samples(wl.W, wl.H, wl.spp, wl.seed, 0, n)
-    o = torch.full((n, 4), float("nan"), device="cuda")
-    d = torch.full((n, 4), float("nan"), device="cuda")
+    rays = torch.full((n, 8), float("nan"), device="cuda")
     cam.reset_stats()
-    cam.create_rays(s, seed=wl.seed, first_index=0, out=(o, d))
+    cam.create_rays(s, seed=wl.seed, first_index=0, out=rays)
     torch.cuda.synchronize()
+    o, d = rays[:, :4], rays[:, 4:]
     st = cam.stats()
     assert not torch.isnan(o[:, 3]).any() and not torch.isnan(d[:, 3]).any()
     assert st["rays"] == n and st["success"] + st["vignetted"] == n

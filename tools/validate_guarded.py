@@ -33,16 +33,18 @@ def run(name, wl, n, first, scales):
     s = cam.synth_samples(wl.W, wl.H, wl.spp, wl.seed, first, n)
     cam.set_mode(MODE_EXACT)
     cam.reset_stats()
-    oe, de = cam.create_rays(s, seed=wl.seed, first_index=first)
+    re_ = cam.create_rays(s, seed=wl.seed, first_index=first)
     torch.cuda.synchronize()
+    oe, de = re_[:, :4], re_[:, 4:]
     st_e = cam.stats()
     res = {"workload": name, "samples": n, "first_index": first, "exact_stats": st_e, "scales": {}}
     cam.set_mode(MODE_GUARDED)
     for sc in scales:
         cam.set_guard_scale(sc)
         cam.reset_stats()
-        o, d = cam.create_rays(s, seed=wl.seed, first_index=first)
+        r_ = cam.create_rays(s, seed=wl.seed, first_index=first)
         torch.cuda.synchronize()
+        o, d = r_[:, :4], r_[:, 4:]
         st = cam.stats()
         flips, bad, eo, ed = compare(o, d, oe, de)
         same_stats = all(st[k] == st_e[k] for k in ("rays", "success", "vignetted", "attempts", "element_visits",

@@ -113,21 +113,20 @@ class ZoicCamera:
 
     # -- the hot path ---------------------------------------------------------------------------
     def create_rays(self, samples, seed=0, first_index=0, out=None, stream=None):
-        """camera_create_ray for a CUDA tensor of samples [n, 4] -> (origin_w [n, 4], dir_tries [n, 4])."""
+        """camera_create_ray for a CUDA tensor of samples [n, 4] -> rays [n, 8]: one 32-byte zoicb_ray per row,
+        (origin.xyz, weight, dir.xyz, tries).  `split_rays` gives the two [n, 4] views."""
         import torch
         assert samples.is_cuda and samples.dtype == torch.float32 and samples.is_contiguous()
         assert samples.device.index == self.device
         n = samples.numel() // 4
         if out is None:
-            o = torch.empty((n, 4), dtype=torch.float32, device=samples.device)
-            d = torch.empty((n, 4), dtype=torch.float32, device=samples.device)
-        else:
-            o, d = out
+            out = torch.empty((n, 8), dtype=torch.float32, device=samples.device)
+        assert out.is_contiguous() and out.dtype == torch.float32 and out.numel() == 8 * n
         if stream is None:
             stream = torch.cuda.current_stream(samples.device).cuda_stream
-        capi.check(self.lib.zoicb_generate(self.ctx, samples.data_ptr(), n, first_index, seed,
-                                           o.data_ptr(), d.data_ptr(), C.c_void_p(stream)))
-        return o, d
+        capi.check(self.lib.zoicb_generate(self.ctx, samples.data_ptr(), n, first_index, seed, out.data_ptr(),
+                                           C.c_void_p(stream)))
+        return out
 
     def create_rays_host(self, samples, seed=0, first_index=0, out=None):
         """The same for HOST memory (numpy arrays or CPU tensors; pinned memory is copied directly)."""
@@ -135,12 +134,9 @@ class ZoicCamera:
             return a.data_ptr() if hasattr(a, "data_ptr") else a.ctypes.data
         n = (samples.numel() if hasattr(samples, "numel") else samples.size) // 4
         if out is None:
-            o = np.empty((n, 4), np.float32)
-            d = np.empty((n, 4), np.float32)
-        else:
-            o, d = out
-        capi.check(self.lib.zoicb_generate_host(self.ctx, ptr(samples), n, first_index, seed, ptr(o), ptr(d)))
-        return o, d
+            out = np.empty((n, 8), np.float32)
+        capi.check(self.lib.zoicb_generate_host(self.ctx, ptr(samples), n, first_index, seed, ptr(out)))
+        return out
 
     def synth_samples(self, W, H, spp, seed, first_index, n, out=None, stream=None):
         """Synthetic (sx, sy, lensx, lensy) samples generated on the device."""
@@ -172,6 +168,11 @@ class ZoicCamera:
             self.close()
         except Exception:
             pass
+
+
+def split_rays(rays):
+    """[n, 8] ray records -> (origin_w [n, 4], dir_tries [n, 4]) views."""
+    return rays[:, :4], rays[:, 4:]
 
 
 def kernel_launches():

@@ -24,6 +24,11 @@ class Params(C.Structure):
     ]
 
 
+class Ray(C.Structure):
+    """zoicb_ray: one 32-byte output record."""
+    _fields_ = [("origin", C.c_float * 3), ("weight", C.c_float), ("dir", C.c_float * 3), ("tries", C.c_float)]
+
+
 class Stats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("rays", "success", "vignetted", "total_internal_reflection",
                                           "attempts", "element_visits", "exact_reruns")]
@@ -55,9 +60,9 @@ SYMBOLS = {
     "zoicb_set_mode": (C.c_int, [_P, C.c_int]),
     "zoicb_get_mode": (C.c_int, [_P]),
     "zoicb_set_guard_scale": (C.c_int, [_P, C.c_float]),
-    "zoicb_generate": (C.c_int, [_P, _P, C.c_uint64, C.c_uint64, C.c_uint64, _P, _P, _P]),
-    "zoicb_generate_host": (C.c_int, [_P, _P, C.c_uint64, C.c_uint64, C.c_uint64, _P, _P]),
-    "zoicb_generate_one": (C.c_int, [_P, _P, C.c_uint64, C.c_uint64, _P, _P]),
+    "zoicb_generate": (C.c_int, [_P, _P, C.c_uint64, C.c_uint64, C.c_uint64, _P, _P]),
+    "zoicb_generate_host": (C.c_int, [_P, _P, C.c_uint64, C.c_uint64, C.c_uint64, _P]),
+    "zoicb_generate_one": (C.c_int, [_P, _P, C.c_uint64, C.c_uint64, _P]),
     "zoicb_synth_samples": (C.c_int, [_P, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint64, _P, _P]),
     "zoicb_get_stats": (C.c_int, [_P, C.POINTER(Stats)]),
     "zoicb_reset_stats": (C.c_int, [_P]),

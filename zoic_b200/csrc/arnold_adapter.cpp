@@ -177,14 +177,14 @@ camera_create_ray {
     NodeData* data = (NodeData*)AiNodeGetLocalData(node);
     if (!data->ctx) { output.weight = 0.0f; return; }
     const float sample[4] = {input.sx, input.sy, input.lensx, input.lensy};
-    float o[4], d[4];
+    zoicb_ray r;
     const uint64_t index = data->next_index.fetch_add(1, std::memory_order_relaxed);
-    if (zoicb_generate_one(data->ctx, sample, index, kAdapterSeed, o, d) != ZOICB_OK) { output.weight = 0.0f; return; }
-    output.origin = AtVector(o[0], o[1], o[2]);
-    output.dir = AtVector(d[0], d[1], d[2]);
+    if (zoicb_generate_one(data->ctx, sample, index, kAdapterSeed, &r) != ZOICB_OK) { output.weight = 0.0f; return; }
+    output.origin = AtVector(r.origin[0], r.origin[1], r.origin[2]);
+    output.dir = AtVector(r.dir[0], r.dir[1], r.dir[2]);
     // the batched ABI starts from weight 1; Arnold's incoming weight is multiplied in (reference :1983-1986)
-    output.weight *= o[3];
-    if (d[3] > 0.0f) {  // the reference's derivative workaround for re-sampled rays (:1974-1977)
+    output.weight *= r.weight;
+    if (r.tries > 0.0f) {  // the reference's derivative workaround for re-sampled rays (:1974-1977)
         output.dOdy = output.origin;
         output.dDdy = output.dir;
     }

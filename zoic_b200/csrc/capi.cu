@@ -15,6 +15,8 @@
 
 using namespace zoicb;
 
+static_assert(sizeof(zoicb_ray) == 32 && sizeof(RayRecord) == 32, "a ray is one 32-byte record");
+
 namespace {
 
 thread_local std::string g_last_error;
@@ -56,11 +58,9 @@ struct zoicb_ctx {
     uint64_t chunk = 0;
     cudaStream_t streams[kSlots] = {nullptr, nullptr, nullptr};
     float4* d_in[kSlots] = {nullptr, nullptr, nullptr};
-    float4* d_o[kSlots] = {nullptr, nullptr, nullptr};
-    float4* d_d[kSlots] = {nullptr, nullptr, nullptr};
+    RayRecord* d_r[kSlots] = {nullptr, nullptr, nullptr};
     float4* h_in[kSlots] = {nullptr, nullptr, nullptr};   // pinned staging, only for pageable callers
-    float4* h_o[kSlots] = {nullptr, nullptr, nullptr};
-    float4* h_d[kSlots] = {nullptr, nullptr, nullptr};
+    RayRecord* h_r[kSlots] = {nullptr, nullptr, nullptr};
     std::mutex host_mu;
 };
 
@@ -127,10 +127,9 @@ void free_ctx(zoicb_ctx* c) {
     cudaFree(c->d_stats);
     for (int s = 0; s < zoicb_ctx::kSlots; ++s) {
         if (c->streams[s]) cudaStreamDestroy(c->streams[s]);
-        cudaFree(c->d_in[s]); cudaFree(c->d_o[s]); cudaFree(c->d_d[s]);
+        cudaFree(c->d_in[s]); cudaFree(c->d_r[s]);
         if (c->h_in[s]) cudaFreeHost(c->h_in[s]);
-        if (c->h_o[s]) cudaFreeHost(c->h_o[s]);
-        if (c->h_d[s]) cudaFreeHost(c->h_d[s]);
+        if (c->h_r[s]) cudaFreeHost(c->h_r[s]);
     }
     delete c;
 }
@@ -236,26 +235,28 @@ zoicb_status zoicb_set_guard_scale(zoicb_ctx* ctx, float scale) {
 }
 
 zoicb_status zoicb_generate(zoicb_ctx* ctx, const void* d_samples, uint64_t n, uint64_t first_index, uint64_t rng_seed,
-                            void* d_origin_w, void* d_dir_tries, void* stream) {
+                            zoicb_ray* d_rays, void* stream) {
     if (!ctx) return fail(ZOICB_ERR_INVALID_ARGUMENT, "zoicb_generate: null context");
     if (n == 0) return ZOICB_OK;
-    if (!d_samples || !d_origin_w || !d_dir_tries) return fail(ZOICB_ERR_INVALID_ARGUMENT, "zoicb_generate: null buffer");
+    if (!d_samples || !d_rays) return fail(ZOICB_ERR_INVALID_ARGUMENT, "zoicb_generate: null buffer");
+    if (((uintptr_t)d_rays & 31u) || ((uintptr_t)d_samples & 15u))
+        return fail(ZOICB_ERR_INVALID_ARGUMENT, "zoicb_generate: samples must be 16-byte and rays 32-byte aligned");
     ZCUDA(cudaSetDevice(ctx->device), "cudaSetDevice");
     int launches = 0;
     Workspace ws = {nullptr, nullptr, 0};
     ZCUDA(get_workspace(ctx, (cudaStream_t)stream, n, &ws), "workspace");
     cudaError_t e = launch_generate(ctx->host.state, ctx->mode, (const float4*)d_samples, n, first_index, rng_seed,
-                                    (float4*)d_origin_w, (float4*)d_dir_tries, ctx->d_stats, (cudaStream_t)stream, ws, &launches);
+                                    (RayRecord*)d_rays, ctx->d_stats, (cudaStream_t)stream, ws, &launches);
     count_launches(launches);
     if (e != cudaSuccess) return cuda_fail(e, "zoicb_generate launch");
     return ZOICB_OK;
 }
 
 zoicb_status zoicb_generate_host(zoicb_ctx* ctx, const float* h_samples, uint64_t n, uint64_t first_index,
-                                 uint64_t rng_seed, float* h_origin_w, float* h_dir_tries) {
+                                 uint64_t rng_seed, zoicb_ray* h_rays) {
     if (!ctx) return fail(ZOICB_ERR_INVALID_ARGUMENT, "zoicb_generate_host: null context");
     if (n == 0) return ZOICB_OK;
-    if (!h_samples || !h_origin_w || !h_dir_tries) return fail(ZOICB_ERR_INVALID_ARGUMENT, "zoicb_generate_host: null buffer");
+    if (!h_samples || !h_rays) return fail(ZOICB_ERR_INVALID_ARGUMENT, "zoicb_generate_host: null buffer");
     std::lock_guard<std::mutex> lock(ctx->host_mu);
     ZCUDA(cudaSetDevice(ctx->device), "cudaSetDevice");
     constexpr int K = zoicb_ctx::kSlots;
@@ -264,16 +265,14 @@ zoicb_status zoicb_generate_host(zoicb_ctx* ctx, const float* h_samples, uint64_
         for (int s = 0; s < K; ++s) {
             ZCUDA(cudaStreamCreateWithFlags(&ctx->streams[s], cudaStreamNonBlocking), "cudaStreamCreate");
             ZCUDA(cudaMalloc(&ctx->d_in[s], ctx->chunk * sizeof(float4)), "cudaMalloc(staging)");
-            ZCUDA(cudaMalloc(&ctx->d_o[s], ctx->chunk * sizeof(float4)), "cudaMalloc(staging)");
-            ZCUDA(cudaMalloc(&ctx->d_d[s], ctx->chunk * sizeof(float4)), "cudaMalloc(staging)");
+            ZCUDA(cudaMalloc(&ctx->d_r[s], ctx->chunk * sizeof(RayRecord)), "cudaMalloc(staging)");
         }
     }
-    const bool direct = is_pinned_host(h_samples) && is_pinned_host(h_origin_w) && is_pinned_host(h_dir_tries);
+    const bool direct = is_pinned_host(h_samples) && is_pinned_host(h_rays);
     if (!direct && !ctx->h_in[0]) {
         for (int s = 0; s < K; ++s) {
             ZCUDA(cudaMallocHost(&ctx->h_in[s], ctx->chunk * sizeof(float4)), "cudaMallocHost");
-            ZCUDA(cudaMallocHost(&ctx->h_o[s], ctx->chunk * sizeof(float4)), "cudaMallocHost");
-            ZCUDA(cudaMallocHost(&ctx->h_d[s], ctx->chunk * sizeof(float4)), "cudaMallocHost");
+            ZCUDA(cudaMallocHost(&ctx->h_r[s], ctx->chunk * sizeof(RayRecord)), "cudaMallocHost");
         }
     }
     const uint64_t nchunks = (n + ctx->chunk - 1) / ctx->chunk;
@@ -285,8 +284,7 @@ zoicb_status zoicb_generate_host(zoicb_ctx* ctx, const float* h_samples, uint64_
         if (e != cudaSuccess) return e;
         if (!direct) {
             const uint64_t b = k * ctx->chunk, m = (n - b < ctx->chunk) ? n - b : ctx->chunk;
-            std::memcpy(h_origin_w + 4 * b, ctx->h_o[s], m * sizeof(float4));
-            std::memcpy(h_dir_tries + 4 * b, ctx->h_d[s], m * sizeof(float4));
+            std::memcpy(h_rays + b, ctx->h_r[s], m * sizeof(RayRecord));
         }
         return cudaSuccess;
     };
@@ -299,13 +297,11 @@ zoicb_status zoicb_generate_host(zoicb_ctx* ctx, const float* h_samples, uint64_
         ZCUDA(cudaMemcpyAsync(ctx->d_in[s], src, m * sizeof(float4), cudaMemcpyHostToDevice, ctx->streams[s]), "H2D");
         Workspace ws = {nullptr, nullptr, 0};
         ZCUDA(get_workspace(ctx, ctx->streams[s], m, &ws), "workspace");
-        cudaError_t e = launch_generate(ctx->host.state, ctx->mode, ctx->d_in[s], m, first_index + b, rng_seed, ctx->d_o[s],
-                                        ctx->d_d[s], ctx->d_stats, ctx->streams[s], ws, &launches);
+        cudaError_t e = launch_generate(ctx->host.state, ctx->mode, ctx->d_in[s], m, first_index + b, rng_seed, ctx->d_r[s],
+                                        ctx->d_stats, ctx->streams[s], ws, &launches);
         if (e != cudaSuccess) { count_launches(launches); return cuda_fail(e, "zoicb_generate_host launch"); }
-        float* dst_o = direct ? h_origin_w + 4 * b : (float*)ctx->h_o[s];
-        float* dst_d = direct ? h_dir_tries + 4 * b : (float*)ctx->h_d[s];
-        ZCUDA(cudaMemcpyAsync(dst_o, ctx->d_o[s], m * sizeof(float4), cudaMemcpyDeviceToHost, ctx->streams[s]), "D2H");
-        ZCUDA(cudaMemcpyAsync(dst_d, ctx->d_d[s], m * sizeof(float4), cudaMemcpyDeviceToHost, ctx->streams[s]), "D2H");
+        void* dst = direct ? (void*)(h_rays + b) : (void*)ctx->h_r[s];
+        ZCUDA(cudaMemcpyAsync(dst, ctx->d_r[s], m * sizeof(RayRecord), cudaMemcpyDeviceToHost, ctx->streams[s]), "D2H");
     }
     count_launches(launches);
     for (uint64_t k = (nchunks > (uint64_t)K ? nchunks - K : 0); k < nchunks; ++k) ZCUDA(drain(k), "pipeline drain");
@@ -316,7 +312,7 @@ namespace {
 struct OneShot {  // per-thread resources of zoicb_generate_one
     int device = -1;
     cudaStream_t stream = nullptr;
-    float4* h = nullptr;  // pinned: [0] sample, [1] origin_w, [2] dir_tries
+    float4* h = nullptr;  // pinned: [0] sample, [2..3] the ray record (32-byte aligned)
     float4* d = nullptr;
     ~OneShot() {
         if (device >= 0) {
@@ -331,29 +327,28 @@ thread_local OneShot t_one;
 }  // namespace
 
 zoicb_status zoicb_generate_one(zoicb_ctx* ctx, const float* sample, uint64_t sample_index, uint64_t rng_seed,
-                                float* origin_w, float* dir_tries) {
-    if (!ctx || !sample || !origin_w || !dir_tries) return fail(ZOICB_ERR_INVALID_ARGUMENT, "zoicb_generate_one: null argument");
+                                zoicb_ray* ray) {
+    if (!ctx || !sample || !ray) return fail(ZOICB_ERR_INVALID_ARGUMENT, "zoicb_generate_one: null argument");
     ZCUDA(cudaSetDevice(ctx->device), "cudaSetDevice");
     OneShot& r = t_one;
     if (r.device != ctx->device) {
         if (r.device >= 0) return fail(ZOICB_ERR_UNSUPPORTED, "zoicb_generate_one: one device per calling thread");
         ZCUDA(cudaStreamCreateWithFlags(&r.stream, cudaStreamNonBlocking), "cudaStreamCreate");
-        ZCUDA(cudaMallocHost(&r.h, 3 * sizeof(float4)), "cudaMallocHost");
-        ZCUDA(cudaMalloc(&r.d, 3 * sizeof(float4)), "cudaMalloc");
+        ZCUDA(cudaMallocHost(&r.h, 4 * sizeof(float4)), "cudaMallocHost");
+        ZCUDA(cudaMalloc(&r.d, 4 * sizeof(float4)), "cudaMalloc");
         r.device = ctx->device;
     }
     std::memcpy(&r.h[0], sample, sizeof(float4));
     ZCUDA(cudaMemcpyAsync(&r.d[0], &r.h[0], sizeof(float4), cudaMemcpyHostToDevice, r.stream), "H2D");
     int launches = 0;
     const Workspace ws = {nullptr, nullptr, 0};
-    cudaError_t e = launch_generate(ctx->host.state, ZOICB_MODE_EXACT, &r.d[0], 1, sample_index, rng_seed, &r.d[1], &r.d[2],
-                                    ctx->d_stats, r.stream, ws, &launches);
+    cudaError_t e = launch_generate(ctx->host.state, ZOICB_MODE_EXACT, &r.d[0], 1, sample_index, rng_seed,
+                                    reinterpret_cast<RayRecord*>(&r.d[2]), ctx->d_stats, r.stream, ws, &launches);
     count_launches(launches);
     if (e != cudaSuccess) return cuda_fail(e, "zoicb_generate_one launch");
-    ZCUDA(cudaMemcpyAsync(&r.h[1], &r.d[1], 2 * sizeof(float4), cudaMemcpyDeviceToHost, r.stream), "D2H");
+    ZCUDA(cudaMemcpyAsync(&r.h[2], &r.d[2], 2 * sizeof(float4), cudaMemcpyDeviceToHost, r.stream), "D2H");
     ZCUDA(cudaStreamSynchronize(r.stream), "cudaStreamSynchronize");
-    std::memcpy(origin_w, &r.h[1], sizeof(float4));
-    std::memcpy(dir_tries, &r.h[2], sizeof(float4));
+    std::memcpy(ray, &r.h[2], sizeof(zoicb_ray));
     return ZOICB_OK;
 }
 

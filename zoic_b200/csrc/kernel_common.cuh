@@ -11,6 +11,14 @@ namespace zoicb {
 
 constexpr int kChunk = 2048;   // samples handed to a warp per grab of the global cursor (multiple of 32)
 
+// One output ray = one 32-byte record (zoicb_ray): origin.xyz, weight, dir.xyz, tries.  A ray is written by a
+// single 256-bit store (STG.E.256), i.e. one full 32-byte sector, whatever order rays finish in.
+__device__ __forceinline__ void store_ray(RayRecord* __restrict__ rays, uint64_t idx, float4 o, float4 d) {
+    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(rays + idx), "f"(o.x), "f"(o.y), "f"(o.z),
+                 "f"(o.w), "f"(d.x), "f"(d.y), "f"(d.z), "f"(d.w)
+                 : "memory");
+}
+
 // ------------------------------------------------------------------------------------------------
 // image-based aperture sampling (reference imageData::bokehSample, src/zoic.cpp:420-485)
 // ------------------------------------------------------------------------------------------------
@@ -251,7 +259,7 @@ inline int sm_count() {
 
 // kolb_pool.cu
 cudaError_t launch_kolb_pool(const CameraState& cam, const float4* samples, uint64_t n, uint64_t first_index, uint64_t seed,
-                             float4* origin_w, float4* dir_tries, DeviceStats* stats, cudaStream_t st, const Workspace& ws,
-                             size_t rows_smem, int* launches);
+                             RayRecord* rays, DeviceStats* stats, cudaStream_t st, const Workspace& ws, size_t rows_smem,
+                             int* launches);
 
 }  // namespace zoicb

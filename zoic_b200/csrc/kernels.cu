@@ -19,7 +19,7 @@ namespace zoicb {
 template <int kModel, bool kImage, bool kLut>
 __global__ void __launch_bounds__(256)
 exact_kernel(const __grid_constant__ CameraState cam, const float4* __restrict__ samples, uint64_t n,
-             uint64_t first_index, uint64_t seed, float4* __restrict__ origin_w, float4* __restrict__ dir_tries,
+             uint64_t first_index, uint64_t seed, RayRecord* __restrict__ rays,
              DeviceStats* stats, int stage_rows) {
     BokehView bk;
     if (kImage) bk = stage_bokeh(cam);
@@ -31,8 +31,7 @@ exact_kernel(const __grid_constant__ CameraState cam, const float4* __restrict__
         float4 o4, d4;
         if (kModel == 0) thin_exact_sample<kImage>(cam, bk, s, first_index + i, seed, &o4, &d4, ls);
         else kolb_exact_sample<kImage, kLut>(cam, bk, s, first_index + i, seed, &o4, &d4, ls);
-        __stcs(origin_w + i, o4);
-        __stcs(dir_tries + i, d4);
+        store_ray(rays, i, o4, d4);
     }
     flush_stats(ls, stats);
 }
@@ -46,8 +45,8 @@ exact_kernel(const __grid_constant__ CameraState cam, const float4* __restrict__
 template <bool kImage, bool kLut, bool kQueued>
 __global__ void __launch_bounds__(256, 3)
 kolb_exact_persistent_kernel(const __grid_constant__ CameraState cam, const float4* __restrict__ samples, uint64_t m_direct,
-                             uint64_t first_index, uint64_t seed, float4* __restrict__ origin_w,
-                             float4* __restrict__ dir_tries, DeviceStats* stats, unsigned long long* cursor,
+                             uint64_t first_index, uint64_t seed, RayRecord* __restrict__ rays,
+                             DeviceStats* stats, unsigned long long* cursor,
                              const unsigned long long* __restrict__ queue, const unsigned long long* __restrict__ queue_count,
                              unsigned long long capacity) {
     BokehView bk;
@@ -58,7 +57,7 @@ kolb_exact_persistent_kernel(const __grid_constant__ CameraState cam, const floa
     LocalStats ls = {0, 0, 0, 0, 0, 0, 0};
     unsigned long long m = m_direct;
     if (kQueued) { m = *queue_count; if (m > capacity) m = capacity; }
-    constexpr unsigned kGrab = 256;   // work items per grab of the global cursor
+    constexpr unsigned kGrab = kQueued ? 32 : 256;   // work items per grab of the global cursor (the queue is short: spread it)
     uint64_t cur = 0, end = 0;
     bool exhausted = false, have = false, fresh = false;
     uint64_t idx = 0;
@@ -118,8 +117,7 @@ kolb_exact_persistent_kernel(const __grid_constant__ CameraState cam, const floa
                 if (tries > kMaxTries) { weight = 0.0f; ls.vignetted++; }
                 else ls.success++;
                 weight = xmul(weight, cam.weight_scale);
-                origin_w[idx] = make_float4(-r.o.x, -r.o.y, -r.o.z, weight);
-                dir_tries[idx] = make_float4(-r.d.x, -r.d.y, -r.d.z, (float)tries);
+                store_ray(rays, idx, make_float4(-r.o.x, -r.o.y, -r.o.z, weight), make_float4(-r.d.x, -r.d.y, -r.d.z, (float)tries));
                 have = false;
             }
         }
@@ -135,7 +133,7 @@ kolb_exact_persistent_kernel(const __grid_constant__ CameraState cam, const floa
 template <bool kImage>
 __global__ void __launch_bounds__(256, 4)
 thin_persistent_kernel(const __grid_constant__ CameraState cam, const float4* __restrict__ samples, uint64_t n,
-                       uint64_t first_index, uint64_t seed, float4* __restrict__ origin_w, float4* __restrict__ dir_tries,
+                       uint64_t first_index, uint64_t seed, RayRecord* __restrict__ rays,
                        DeviceStats* stats, int stage_rows, unsigned long long* chunk_counter) {
     BokehView bk;
     if (kImage) bk = stage_bokeh(cam);
@@ -205,8 +203,7 @@ thin_persistent_kernel(const __grid_constant__ CameraState cam, const float4* __
                 if (tries > kMaxTries) { weight = 0.0f; ls.vignetted++; }
                 else ls.success++;
                 weight = xmul(weight, cam.weight_scale);
-                __stcs(origin_w + idx, make_float4(origin.x, origin.y, origin.z, weight));
-                __stcs(dir_tries + idx, make_float4(dir.x, dir.y, -dir.z, (float)tries));
+                store_ray(rays, idx, make_float4(origin.x, origin.y, origin.z, weight), make_float4(dir.x, dir.y, -dir.z, (float)tries));
                 ls.rays++;
                 have = false;
             }
@@ -292,16 +289,16 @@ static unsigned grid_for(uint64_t n, int threads, int ctas_per_sm) {
 
 template <int kModel, bool kImage, bool kLut>
 static cudaError_t launch_variant(const CameraState& cam, int mode, const float4* samples, uint64_t n, uint64_t first_index,
-                                  uint64_t seed, float4* origin_w, float4* dir_tries, DeviceStats* stats, cudaStream_t st,
+                                  uint64_t seed, RayRecord* rays, DeviceStats* stats, cudaStream_t st,
                                   const Workspace& ws, size_t smem, int stage, int* launches) {
     const int threads = 256;
     if (mode == 1 && kModel == 1) {  // guarded fast path + exact re-run of the undecided samples
         cudaError_t e = cudaMemsetAsync(ws.counters, 0, 4 * sizeof(unsigned long long), st);
         if (e != cudaSuccess) return e;
-        e = launch_kolb_pool(cam, samples, n, first_index, seed, origin_w, dir_tries, stats, st, ws, smem, launches);
+        e = launch_kolb_pool(cam, samples, n, first_index, seed, rays, stats, st, ws, smem, launches);
         if (e != cudaSuccess) return e;
         kolb_exact_persistent_kernel<kImage, kLut, true><<<(unsigned)sm_count() * 3, threads, smem, st>>>(
-            cam, samples, 0, first_index, seed, origin_w, dir_tries, stats, ws.counters + 2, ws.queue, ws.counters + 1,
+            cam, samples, 0, first_index, seed, rays, stats, ws.counters + 2, ws.queue, ws.counters + 1,
             ws.capacity);
         if (launches) *launches += 1;
         return cudaGetLastError();
@@ -310,26 +307,26 @@ static cudaError_t launch_variant(const CameraState& cam, int mode, const float4
         cudaError_t e = cudaMemsetAsync(ws.counters, 0, 4 * sizeof(unsigned long long), st);
         if (e != cudaSuccess) return e;
         kolb_exact_persistent_kernel<kImage, kLut, false><<<(unsigned)sm_count() * 3, threads, smem, st>>>(
-            cam, samples, n, first_index, seed, origin_w, dir_tries, stats, ws.counters + 2, nullptr, nullptr, 0);
+            cam, samples, n, first_index, seed, rays, stats, ws.counters + 2, nullptr, nullptr, 0);
         if (launches) *launches += 1;
         return cudaGetLastError();
     }
     if (mode == 1 && kModel == 0 && cam.thin.use_dof && cam.thin.use_ov) {  // retry loop present: persistent schedule
         cudaError_t e = cudaMemsetAsync(ws.counters, 0, 4 * sizeof(unsigned long long), st);
         if (e != cudaSuccess) return e;
-        thin_persistent_kernel<kImage><<<(unsigned)sm_count() * 4, threads, smem, st>>>(cam, samples, n, first_index, seed, origin_w,
-                                                                                      dir_tries, stats, stage, ws.counters);
+        thin_persistent_kernel<kImage><<<(unsigned)sm_count() * 4, threads, smem, st>>>(cam, samples, n, first_index, seed, rays,
+                                                                                      stats, stage, ws.counters);
         if (launches) *launches += 1;
         return cudaGetLastError();
     }
     exact_kernel<kModel, kImage, kLut><<<grid_for(n, threads, 8), threads, smem, st>>>(cam, samples, n, first_index, seed,
-                                                                                     origin_w, dir_tries, stats, stage);
+                                                                                     rays, stats, stage);
     if (launches) *launches += 1;
     return cudaGetLastError();
 }
 
 cudaError_t launch_generate(const CameraState& cam, int mode, const float4* samples, uint64_t n, uint64_t first_index,
-                            uint64_t seed, float4* origin_w, float4* dir_tries, DeviceStats* stats, cudaStream_t st,
+                            uint64_t seed, RayRecord* rays, DeviceStats* stats, cudaStream_t st,
                             const Workspace& ws, int* launches) {
     if (n == 0) return cudaSuccess;
     if (n < 8192) mode = 0;  // a persistent grid does not pay for a handful of samples; the exact kernel is also bit-exact
@@ -340,7 +337,7 @@ cudaError_t launch_generate(const CameraState& cam, int mode, const float4* samp
         smem = (size_t)cam.bokeh.h * 8;
         stage = 1;
     }
-#define ZL(M, I, U) launch_variant<M, I, U>(cam, mode, samples, n, first_index, seed, origin_w, dir_tries, stats, st, ws, smem, stage, launches)
+#define ZL(M, I, U) launch_variant<M, I, U>(cam, mode, samples, n, first_index, seed, rays, stats, st, ws, smem, stage, launches)
     if (cam.lens_model == 0) return image ? ZL(0, true, false) : ZL(0, false, false);
     const bool lut = cam.lens.use_lut != 0;
     if (image) return lut ? ZL(1, true, true) : ZL(1, true, false);

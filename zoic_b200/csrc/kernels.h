@@ -7,6 +7,8 @@
 
 namespace zoicb {
 
+struct alignas(32) RayRecord { float4 origin_w; float4 dir_tries; };   // = zoicb_ray (include/zoicb.h)
+
 // Per-stream scratch: counters[0] = chunk cursor of the main kernel, counters[1] = number of queued (undecided)
 // sample indices, counters[2] = work cursor of the exact persistent kernel, counters[3] spare;
 // queue[capacity] = the undecided sample indices.
@@ -17,8 +19,8 @@ struct Workspace {
 };
 
 cudaError_t launch_generate(const CameraState& cam, int mode, const float4* samples, uint64_t n, uint64_t first_index,
-                            uint64_t seed, float4* origin_w, float4* dir_tries, DeviceStats* stats, cudaStream_t st,
-                            const Workspace& ws, int* launches);
+                            uint64_t seed, RayRecord* rays, DeviceStats* stats, cudaStream_t st, const Workspace& ws,
+                            int* launches);
 cudaError_t launch_synth(uint32_t W, uint32_t H, uint32_t spp, uint64_t seed, uint64_t first_index, uint64_t n,
                          float4* out, cudaStream_t st, int* launches);
 cudaError_t launch_lut_trace(const LensState& L, const float* d_film_x, int n_film, int per_film, const uint32_t* d_draws,

@@ -90,7 +90,7 @@ __device__ __forceinline__ int fast_march_range(const LensState& L, float gscale
 template <int kN, bool kImage, bool kLut, bool kInner>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, ZOICB_POOL_CTAS)
 kolb_pool_kernel(const __grid_constant__ CameraState cam, const float4* __restrict__ samples, uint32_t n,
-                 uint64_t first_index, uint64_t seed, float4* __restrict__ origin_w, float4* __restrict__ dir_tries,
+                 uint64_t first_index, uint64_t seed, RayRecord* __restrict__ rays,
                  DeviceStats* stats, unsigned long long* chunk_counter, unsigned long long* queue,
                  unsigned long long* queue_count, unsigned long long capacity, uint64_t queue_base) {
     // dynamic shared memory: [bokeh row tables (2h floats, 16-byte aligned)] [one WarpPool per warp]
@@ -129,10 +129,7 @@ kolb_pool_kernel(const __grid_constant__ CameraState cam, const float4* __restri
             if (tries > (unsigned)kMaxTries) { weight = 0.0f; ls.vignetted++; ux = 0.0f; uy = 0.0f; uz = 1.0f; }
             else ls.success++;
             weight *= cam.weight_scale;
-            // plain (write-back) stores: the two 16-byte halves of a 32-byte sector are written by different lanes at
-            // different times and must meet in L2; streaming stores get evicted half-written and cost a read-modify-write
-            origin_w[idx] = make_float4(-ox, -oy, -oz, weight);
-            dir_tries[idx] = make_float4(-ux, -uy, -uz, (float)tries);
+            store_ray(rays, idx, make_float4(-ox, -oy, -oz, weight), make_float4(-ux, -uy, -uz, (float)tries));
             ls.rays++;
             ls.attempts += tries + 1;
             ls.visits += pk_visits(packed);
@@ -151,8 +148,7 @@ kolb_pool_kernel(const __grid_constant__ CameraState cam, const float4* __restri
                 } else {  // queue full: settle it here, exactly
                     float4 o4, d4;
                     kolb_exact_sample<kImage, kLut>(cam, bk, samples[idx], first_index + idx, seed, &o4, &d4, ls);
-                    __stcs(origin_w + idx, o4);
-                    __stcs(dir_tries + idx, d4);
+                    store_ray(rays, idx, o4, d4);
                     ls.reruns++;
                 }
             }
@@ -293,7 +289,7 @@ kolb_pool_kernel(const __grid_constant__ CameraState cam, const float4* __restri
 // ------------------------------------------------------------------------------------------------
 template <bool kImage, bool kLut>
 static cudaError_t launch_pool_variant(const CameraState& cam, const float4* samples, uint64_t n, uint64_t first_index,
-                                       uint64_t seed, float4* origin_w, float4* dir_tries, DeviceStats* stats, cudaStream_t st,
+                                       uint64_t seed, RayRecord* rays, DeviceStats* stats, cudaStream_t st,
                                        const Workspace& ws, size_t rows_smem, int* launches) {
     const unsigned grid = (unsigned)sm_count() * ZOICB_POOL_CTAS;  // persistent: ZOICB_POOL_CTAS CTAs of 8 warps per SM
     const int threads = kWarpsPerCta * 32;
@@ -311,7 +307,7 @@ static cudaError_t launch_pool_variant(const CameraState& cam, const float4* sam
         cudaFuncSetAttribute(kolb_pool_kernel<N, kImage, kLut, INNER>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
                              (int)pool_smem);                                                                            \
         kolb_pool_kernel<N, kImage, kLut, INNER><<<grid, threads, pool_smem, st>>>(                                      \
-            cam, samples + b, m, first_index + b, seed, origin_w + b, dir_tries + b, stats, ws.counters, ws.queue,       \
+            cam, samples + b, m, first_index + b, seed, rays + b, stats, ws.counters, ws.queue,       \
             ws.counters + 1, ws.capacity, b);                                                                            \
     } while (0)
 #define ZPN(N) do { if (cam.lens.inner_retry) ZP(N, true); else ZP(N, false); } while (0)
@@ -331,10 +327,10 @@ static cudaError_t launch_pool_variant(const CameraState& cam, const float4* sam
 }
 
 cudaError_t launch_kolb_pool(const CameraState& cam, const float4* samples, uint64_t n, uint64_t first_index, uint64_t seed,
-                             float4* origin_w, float4* dir_tries, DeviceStats* stats, cudaStream_t st, const Workspace& ws,
-                             size_t rows_smem, int* launches) {
+                             RayRecord* rays, DeviceStats* stats, cudaStream_t st, const Workspace& ws, size_t rows_smem,
+                             int* launches) {
     const bool image = cam.use_image != 0, lut = cam.lens.use_lut != 0;
-#define ZL(I, U) launch_pool_variant<I, U>(cam, samples, n, first_index, seed, origin_w, dir_tries, stats, st, ws, rows_smem, launches)
+#define ZL(I, U) launch_pool_variant<I, U>(cam, samples, n, first_index, seed, rays, stats, st, ws, rows_smem, launches)
     if (image) return lut ? ZL(true, true) : ZL(true, false);
     return lut ? ZL(false, true) : ZL(false, false);
 #undef ZL

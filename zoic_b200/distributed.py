@@ -14,24 +14,21 @@ def shard_range(n, rank, world):
     return first, base + (1 if rank < extra else 0)
 
 
-def gather_rays(origin_w, dir_tries, group=None):
-    """All-gather the per-rank ray buffers ([count, 4] each) into the full [n, 4] buffers, in rank order.
-    Shards may differ by one row (shard_range), so rows are padded to the largest shard for the collective."""
+def gather_rays(rays, group=None):
+    """All-gather the per-rank ray buffers ([count, 8], one 32-byte record per row) into the full [n, 8] buffer,
+    in rank order.  Shards may differ by one row (shard_range), so rows are padded to the largest shard."""
     import torch
     import torch.distributed as dist
     world = dist.get_world_size(group)
-    counts = [torch.zeros(1, dtype=torch.int64, device=origin_w.device) for _ in range(world)]
-    dist.all_gather(counts, torch.tensor([origin_w.shape[0]], dtype=torch.int64, device=origin_w.device), group=group)
+    counts = [torch.zeros(1, dtype=torch.int64, device=rays.device) for _ in range(world)]
+    dist.all_gather(counts, torch.tensor([rays.shape[0]], dtype=torch.int64, device=rays.device), group=group)
     counts = [int(c.item()) for c in counts]
     m = max(counts)
-
-    def one(t):
-        pad = t if t.shape[0] == m else torch.cat([t, t.new_zeros((m - t.shape[0], 4))])
-        out = [torch.empty((m, 4), dtype=t.dtype, device=t.device) for _ in range(world)]
-        dist.all_gather(out, pad.contiguous(), group=group)
-        return torch.cat([out[r][:counts[r]] for r in range(world)])
-
-    return one(origin_w), one(dir_tries)
+    width = rays.shape[1]
+    pad = rays if rays.shape[0] == m else torch.cat([rays, rays.new_zeros((m - rays.shape[0], width))])
+    out = [torch.empty((m, width), dtype=rays.dtype, device=rays.device) for _ in range(world)]
+    dist.all_gather(out, pad.contiguous(), group=group)
+    return torch.cat([out[r][:counts[r]] for r in range(world)])
 
 
 def reduce_stats(stats, device, group=None):
