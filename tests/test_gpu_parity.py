@@ -340,3 +340,43 @@ def test_large_batch_spans_many_chunks_and_keeps_counters(port):
     assert st["success"] == int((o[:, 3] != 0).sum()) and st["vignetted"] == int((o[:, 3] == 0).sum())
     assert st["attempts"] == n + int(d[:, 3].sum())
     cam.close()
+
+
+def test_random_cameras_sweep(port):
+    """Random node parameters over their documented ranges (src/zoic.mtd): EXACT is bit-identical, GUARDED has
+    zero path flips and stays inside the tolerance, for every lens table and both lens models."""
+    from zoic_b200 import ZoicCamera, MODE_EXACT, MODE_GUARDED
+    from zoic_b200.workloads import LENSES, lens_path
+    rng = np.random.default_rng(2024)
+    lenses = sorted(LENSES)
+    worst = {"o": 0.0, "d": 0.0}
+    for trial in range(24):
+        if trial % 4 == 3:
+            kw = dict(lensModel=0, focalLength=float(rng.uniform(1.5, 10.0)), fStop=float(rng.uniform(1.0, 16.0)),
+                      focalDistance=float(rng.uniform(20.0, 500.0)),
+                      opticalVignettingDistance=float(rng.choice([0.0, rng.uniform(0.5, 6.0)])),
+                      opticalVignettingRadius=float(rng.uniform(0.5, 2.0)), exposureControl=float(rng.uniform(-2, 2)))
+        else:
+            lens = lenses[trial % len(lenses)]
+            native = 1.0 if "fisheye" in lens else 5.0
+            kw = dict(lensModel=1, lensDataPath=lens_path(lens), focalLength=float(native * rng.uniform(0.6, 1.8)),
+                      fStop=float(rng.uniform(1.2, 11.0)), focalDistance=float(rng.uniform(25.0, 800.0)),
+                      kolbSamplingLUT=int(rng.random() < 0.8), exposureControl=float(rng.uniform(-1, 1)),
+                      sensorWidth=float(rng.choice([3.6, 2.4, 1.8])))
+        ref = port.PortCamera(**kw)
+        s = random_samples(60_000, seed=100 + trial)
+        o2, d2, st2 = ref.generate(s, seed=trial, first_index=1 << 33, nthreads=8)
+        for mode in (MODE_EXACT, MODE_GUARDED):
+            cam = ZoicCamera(mode=mode, **kw)
+            o, d, st = _run_gpu(cam, s, seed=trial, first_index=1 << 33)
+            if mode == MODE_EXACT:
+                assert bits_equal(o, o2) and bits_equal(d, d2), kw
+            else:
+                res = compare_rays(o, d, o2, d2)
+                assert res["path_flips"] == 0 and res["out_of_tol"] == 0, (kw, res)
+                worst["o"] = max(worst["o"], res["max_origin_err"])
+                worst["d"] = max(worst["d"], res["max_dir_err"])
+            assert st["attempts"] == st2["attempts"] and st["vignetted"] == st2["vignetted"], kw
+            cam.close()
+        ref.close()
+    assert worst["o"] < 1e-5 and worst["d"] < 1e-5
