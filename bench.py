@@ -165,6 +165,7 @@ def main():
     ap.add_argument("--workload", default="headline")
     ap.add_argument("--mode", default="default", choices=["default", "exact", "guarded"])
     ap.add_argument("--samples", type=int, default=0, help="override samples per GPU per step (debug)")
+    ap.add_argument("--spp", type=int, default=0, help="override samples per pixel (profiling: a small batch that still covers the whole film)")
     ap.add_argument("--e2e-samples", type=int, default=1 << 26)
     ap.add_argument("--cpu-samples", type=int, default=1 << 22, help="CPU baseline sample size (all cores)")
     ap.add_argument("--gather", action="store_true", help="N > 1: also time generation + NCCL all-gather of a 2^26-ray tile")
@@ -174,6 +175,9 @@ def main():
 
     from zoic_b200 import workloads
     wl = workloads.BY_NAME[args.workload]()
+    if args.spp:
+        wl.spp = args.spp
+        wl.name += " [spp overridden: %d]" % args.spp
     if args.impl == "reference":
         run_reference_arm(args, wl)
         return

@@ -10,10 +10,11 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
-LIBDIR = os.path.join(HERE, "lib")
+# ZOICB_LIBDIR: load (and build into) another directory -- A/B variants made by tools/build_variants.py
+LIBDIR = os.environ.get("ZOICB_LIBDIR") or os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libzoicb.so")
 
-SOURCES = ["capi.cu", "kernels.cu", "kolb_pool.cu", "host_setup.cpp"]
+SOURCES = ["capi.cu", "kernels.cu", "kolb_pool.cu", "kolb_pool2.cu", "host_setup.cpp"]
 ADAPTER = "arnold_adapter.cpp"
 PLUGIN = os.path.join(LIBDIR, "libzoic_arnold.so")
 HEADERS = ["camera_state.h", "lens_math.cuh", "host_setup.h", "kernels.h", "kernel_common.cuh",

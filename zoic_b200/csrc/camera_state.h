@@ -15,7 +15,7 @@ constexpr int kMaxTries = 25;  // reference src/zoic.cpp:1767
 
 // One refracting surface, rear element (nearest the sensor) first.  Everything the march needs per
 // element visit is precomputed once on the host with the reference's own rounding.
-struct Element {
+struct alignas(16) Element {
     float center;     // z of the sphere centre (src/zoic.cpp:963-969)
     float radius;     // signed radius of curvature R, cm (the stop is the R = 9999.9 "sphere")
     float radius2;    // fl(R*R)
@@ -53,7 +53,7 @@ struct LensState {
     int32_t pad1, pad2;
     float lut_scale[kLutSize];  // boundingBox2d::getMaxScale() per LUT entry (src/zoic.cpp:503-517)
     float lut_cx[kLutSize];     // boundingBox2d::getCentroid().x per LUT entry
-    Element e[kMaxElements];
+    Element e[kMaxElements];    // 16-byte aligned: the packed kernel reads an element as four 128-bit constant loads
 };
 
 struct ThinState {

@@ -261,5 +261,9 @@ inline int sm_count() {
 cudaError_t launch_kolb_pool(const CameraState& cam, const float4* samples, uint64_t n, uint64_t first_index, uint64_t seed,
                              RayRecord* rays, DeviceStats* stats, cudaStream_t st, const Workspace& ws, size_t rows_smem,
                              int* launches);
+// kolb_pool2.cu (two rays per lane, packed fp32)
+cudaError_t launch_kolb_pool2(const CameraState& cam, const float4* samples, uint64_t n, uint64_t first_index, uint64_t seed,
+                              RayRecord* rays, DeviceStats* stats, cudaStream_t st, const Workspace& ws, size_t rows_smem,
+                              int* launches);
 
 }  // namespace zoicb

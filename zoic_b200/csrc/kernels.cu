@@ -8,6 +8,7 @@
 // writes 2 x 512 B contiguous.  Camera constants travel as a __grid_constant__ kernel parameter.
 #include <cuda_runtime.h>
 #include <math_constants.h>
+#include <stdlib.h>
 
 #include "kernel_common.cuh"
 
@@ -295,7 +296,10 @@ static cudaError_t launch_variant(const CameraState& cam, int mode, const float4
     if (mode == 1 && kModel == 1) {  // guarded fast path + exact re-run of the undecided samples
         cudaError_t e = cudaMemsetAsync(ws.counters, 0, 4 * sizeof(unsigned long long), st);
         if (e != cudaSuccess) return e;
-        e = launch_kolb_pool(cam, samples, n, first_index, seed, rays, stats, st, ws, smem, launches);
+        // ZOICB_POOL=1 selects the scalar (one ray per lane) pool kernel, kept for A/B measurements
+        static const bool scalar_pool = [] { const char* v = getenv("ZOICB_POOL"); return v && v[0] == '1'; }();
+        e = scalar_pool ? launch_kolb_pool(cam, samples, n, first_index, seed, rays, stats, st, ws, smem, launches)
+                        : launch_kolb_pool2(cam, samples, n, first_index, seed, rays, stats, st, ws, smem, launches);
         if (e != cudaSuccess) return e;
         kolb_exact_persistent_kernel<kImage, kLut, true><<<(unsigned)sm_count() * 3, threads, smem, st>>>(
             cam, samples, 0, first_index, seed, rays, stats, ws.counters + 2, ws.queue, ws.counters + 1,
