@@ -11,6 +11,7 @@
  *   zoicb_generate_host the same, host buffers in / out          src/zoic.cpp:1752-1990
  *   zoicb_get_stats     the counters printed by node_finish      src/zoic.cpp:1729-1732
  *   zoicb_destroy       node_finish                              src/zoic.cpp:1723-1749
+ *   zoicb_transform_rays  (the renderer's camera-to-world step after camera_create_ray; nothing in zoic)
  *   zoicb_params        the 14 node parameters                   src/zoic.cpp:1547-1562
  * The Arnold-shaped per-sample surface (NodeLoader + the six node callbacks, src/zoic.cpp:1999-2007)
  * is exported by the same library from zoic_b200/csrc/arnold_adapter.cpp on top of these calls.
@@ -160,6 +161,14 @@ ZOICB_API zoicb_status zoicb_generate_host(zoicb_ctx* ctx, const float* h_sample
  * call, i.e. a compatibility path -- throughput comes from the batched entry points above. */
 ZOICB_API zoicb_status zoicb_generate_one(zoicb_ctx* ctx, const float* sample, uint64_t sample_index,
                                           uint64_t rng_seed, zoicb_ray* ray);
+
+/* Camera -> world epilogue: what the renderer does with every ray right after
+ * camera_create_ray (the reference's output is in camera space, src/zoic.cpp:1845, :1960-1961).  m3x4 is a
+ * row-major 3x4 camera-to-world matrix in HOST memory; origin' = M (origin, 1), dir' = M3x3 dir, weight and
+ * tries pass through.  d_rays / d_out are device pointers (32-byte aligned; d_out may equal d_rays).
+ * Arithmetic: one fma chain per component, innermost term first (zoic_b200/csrc/kernels.cu). */
+ZOICB_API zoicb_status zoicb_transform_rays(zoicb_ctx* ctx, const zoicb_ray* d_rays, uint64_t n, const float* m3x4,
+                                            zoicb_ray* d_out, void* stream);
 
 /* Synthetic camera samples for benchmarks and parity tests: sample index i is
  * pixel-major / spp-minor over a W x H image, four 24-bit uniforms from a counter hash of (seed, i). */

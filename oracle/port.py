@@ -50,6 +50,7 @@ def load():
     lib.zport_synth_samples.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint64,
                                         C.c_void_p]
     lib.zport_sample_stream.argtypes = [C.c_uint64, C.c_uint64, C.c_void_p]
+    lib.zport_transform_rays.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
     lib.zport_get_constants.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
     lib.zport_get_bokeh_tables.argtypes = [C.c_void_p] * 5
     _lib = lib
@@ -59,6 +60,15 @@ def load():
 def synth_samples(W, H, spp, seed, first_index, n):
     out = np.empty((n, 4), np.float32)
     load().zport_synth_samples(W, H, spp, seed, first_index, n, out.ctypes.data)
+    return out
+
+
+def transform_rays(rays, camera_to_world):
+    """CPU statement of the camera -> world epilogue contract (include/zoicb.h: zoicb_transform_rays)."""
+    rays = np.ascontiguousarray(rays, np.float32).reshape(-1, 8)
+    m = np.ascontiguousarray(np.asarray(camera_to_world, np.float32).reshape(12))
+    out = np.empty_like(rays)
+    load().zport_transform_rays(rays.ctypes.data, rays.shape[0], m.ctypes.data, out.ctypes.data)
     return out
 
 

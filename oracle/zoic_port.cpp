@@ -791,6 +791,25 @@ void zport_sample_stream(uint64_t seed, uint64_t index, uint32_t out[4]) {
     out[0] = s.x; out[1] = s.y; out[2] = s.z; out[3] = s.w;
 }
 
+// Camera -> world epilogue.  Nothing in the reference computes this (Arnold applies the camera
+// matrix itself after camera_create_ray; the reference's output is camera space, src/zoic.cpp:1845, :1960-1961),
+// so this is the CPU statement of the contract in include/zoicb.h: one fma chain per component, innermost term
+// first.  rays: n x 8 floats (origin.xyz, weight, dir.xyz, tries); m: row-major 3x4.
+void zport_transform_rays(const float* rays, uint64_t n, const float* m, float* out) {
+    for (uint64_t i = 0; i < n; ++i) {
+        const float* r = rays + 8 * i;
+        float* o = out + 8 * i;
+        const float ox = r[0], oy = r[1], oz = r[2], dx = r[4], dy = r[5], dz = r[6];
+        for (int k = 0; k < 3; ++k) {
+            const float* mr = m + 4 * k;
+            o[k] = fmaf(mr[0], ox, fmaf(mr[1], oy, fmaf(mr[2], oz, mr[3])));
+            o[4 + k] = fmaf(mr[0], dx, fmaf(mr[1], dy, mr[2] * dz));
+        }
+        o[3] = r[3];
+        o[7] = r[7];
+    }
+}
+
 // Derived camera state for host-side parity tests.
 //   scalars[16]: fov, tan_fov, apertureRadius, userApertureRadius, originShift, apertureDistance,
 //                focalLengthRatio, tracedFocalLength[0..1], principalPlane[0..1], focalPoint[0..1],

@@ -380,3 +380,44 @@ def test_random_cameras_sweep(port):
             cam.close()
         ref.close()
     assert worst["o"] < 1e-5 and worst["d"] < 1e-5
+
+
+def test_camera_to_world_epilogue_matches_the_contract(port):
+    """zoicb_transform_rays against the CPU statement of its arithmetic, bit for bit; in place and
+    out of place; weight / tries untouched; identity matrix is the identity; empty batch is a no-op."""
+    from zoic_b200 import ZoicCamera
+    from zoic_b200.workloads import config2
+    wl = config2()
+    cam = ZoicCamera(**wl.params)
+    n = 300_001   # not a multiple of anything
+    s = cam.synth_samples(wl.W, wl.H, wl.spp, wl.seed, 5_000_000, n)
+    rays = cam.create_rays(s, seed=wl.seed, first_index=5_000_000)
+    torch.cuda.synchronize()
+    host = rays.cpu().numpy()
+    rng = np.random.default_rng(3)
+    # a rigid camera placement (rotation about a skew axis + translation in cm) and a general affine matrix
+    a = rng.normal(size=3); a /= np.linalg.norm(a); th = 0.7
+    K = np.array([[0, -a[2], a[1]], [a[2], 0, -a[0]], [-a[1], a[0], 0]])
+    R = np.eye(3) + np.sin(th) * K + (1 - np.cos(th)) * K @ K
+    rigid = np.concatenate([R, np.array([[120.0], [-35.5], [900.25]])], axis=1).astype(np.float32)
+    general = rng.normal(size=(3, 4)).astype(np.float32)
+    for m in (rigid, general):
+        want = port.transform_rays(host, m)
+        got = cam.transform_rays(rays, m)
+        torch.cuda.synchronize()
+        assert bits_equal(got.cpu().numpy(), want)
+        assert bits_equal(got.cpu().numpy()[:, 3], host[:, 3]) and bits_equal(got.cpu().numpy()[:, 7], host[:, 7])
+    # rigid motion keeps directions unit length
+    g = cam.transform_rays(rays, rigid).cpu().numpy()
+    live = host[:, 3] != 0
+    assert np.abs(np.linalg.norm(g[live, 4:7].astype(np.float64), axis=1) - 1.0).max() < 1e-6
+    ident = np.eye(3, 4, dtype=np.float32)
+    same = cam.transform_rays(rays, ident).cpu().numpy()
+    # identity: fma(1, x, fma(0, y, fma(0, z, 0))) = x exactly (also for -0.0 + 0.0 = +0.0: compare values)
+    assert np.array_equal(same[:, :3], host[:, :3]) and np.array_equal(same[:, 4:7], host[:, 4:7])
+    inplace = rays.clone()
+    cam.transform_rays(inplace, general, out=inplace)
+    torch.cuda.synchronize()
+    assert bits_equal(inplace.cpu().numpy(), port.transform_rays(host, general))
+    cam.transform_rays(rays[:0], general)
+    cam.close()

@@ -86,3 +86,21 @@ def test_synthetic_samples_definition(port):
     # any slice can be regenerated independently
     part = port.synth_samples(W, H, spp, 0x200C, 1000, 500)
     assert bits_equal(part, s[1000:1500])
+
+
+def test_epilogue_contract_statement_is_an_affine_map(port):
+    """oracle.port.transform_rays (the CPU statement of zoicb_transform_rays): agrees with a float64 matrix product
+    to fp32 rounding, passes weight / tries through, and composes with its inverse to the identity."""
+    rng = np.random.default_rng(5)
+    rays = rng.normal(size=(5000, 8)).astype(np.float32)
+    m = rng.normal(size=(3, 4)).astype(np.float32)
+    out = port.transform_rays(rays, m)
+    M = m.astype(np.float64)
+    o = rays[:, :3].astype(np.float64) @ M[:, :3].T + M[:, 3]
+    d = rays[:, 4:7].astype(np.float64) @ M[:, :3].T
+    assert np.abs(out[:, :3] - o).max() < 2e-6 * max(1.0, np.abs(o).max())
+    assert np.abs(out[:, 4:7] - d).max() < 2e-6 * max(1.0, np.abs(d).max())
+    assert np.array_equal(out[:, 3], rays[:, 3]) and np.array_equal(out[:, 7], rays[:, 7])
+    inv = np.linalg.inv(np.vstack([M, [0, 0, 0, 1]]))[:3].astype(np.float32)
+    back = port.transform_rays(out, inv)
+    assert np.abs(back[:, :3] - rays[:, :3]).max() < 1e-3 and np.abs(back[:, 4:7] - rays[:, 4:7]).max() < 1e-3

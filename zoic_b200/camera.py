@@ -138,6 +138,21 @@ class ZoicCamera:
         capi.check(self.lib.zoicb_generate_host(self.ctx, ptr(samples), n, first_index, seed, ptr(out)))
         return out
 
+    def transform_rays(self, rays, camera_to_world, out=None, stream=None):
+        """Camera -> world epilogue: rays [n, 8] on the device, camera_to_world a 3x4 row-major
+        matrix (any array-like of 12 floats); returns the transformed records (in place when out is rays)."""
+        import torch
+        assert rays.is_cuda and rays.dtype == torch.float32 and rays.is_contiguous()
+        m = np.ascontiguousarray(np.asarray(camera_to_world, dtype=np.float32).reshape(12))
+        n = rays.numel() // 8
+        if out is None:
+            out = torch.empty_like(rays)
+        if stream is None:
+            stream = torch.cuda.current_stream(rays.device).cuda_stream
+        capi.check(self.lib.zoicb_transform_rays(self.ctx, rays.data_ptr(), n, m.ctypes.data, out.data_ptr(),
+                                                 C.c_void_p(stream)))
+        return out
+
     def synth_samples(self, W, H, spp, seed, first_index, n, out=None, stream=None):
         """Synthetic (sx, sy, lensx, lensy) samples generated on the device."""
         import torch

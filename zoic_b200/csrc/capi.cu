@@ -352,6 +352,21 @@ zoicb_status zoicb_generate_one(zoicb_ctx* ctx, const float* sample, uint64_t sa
     return ZOICB_OK;
 }
 
+zoicb_status zoicb_transform_rays(zoicb_ctx* ctx, const zoicb_ray* d_rays, uint64_t n, const float* m3x4, zoicb_ray* d_out,
+                                  void* stream) {
+    if (!ctx) return fail(ZOICB_ERR_INVALID_ARGUMENT, "zoicb_transform_rays: null context");
+    if (n == 0) return ZOICB_OK;
+    if (!d_rays || !d_out || !m3x4) return fail(ZOICB_ERR_INVALID_ARGUMENT, "zoicb_transform_rays: null argument");
+    if (((uintptr_t)d_rays & 31u) || ((uintptr_t)d_out & 31u))
+        return fail(ZOICB_ERR_INVALID_ARGUMENT, "zoicb_transform_rays: rays must be 32-byte aligned");
+    ZCUDA(cudaSetDevice(ctx->device), "cudaSetDevice");
+    int launches = 0;
+    cudaError_t e = launch_transform(m3x4, (const RayRecord*)d_rays, n, (RayRecord*)d_out, (cudaStream_t)stream, &launches);
+    count_launches(launches);
+    if (e != cudaSuccess) return cuda_fail(e, "zoicb_transform_rays launch");
+    return ZOICB_OK;
+}
+
 zoicb_status zoicb_synth_samples(zoicb_ctx* ctx, uint32_t W, uint32_t H, uint32_t spp, uint64_t seed, uint64_t first_index,
                                  uint64_t n, void* d_samples, void* stream) {
     if (!ctx) return fail(ZOICB_ERR_INVALID_ARGUMENT, "zoicb_synth_samples: null context");

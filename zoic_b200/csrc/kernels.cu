@@ -264,6 +264,42 @@ lut_trace_kernel(const __grid_constant__ LensState L, const float* __restrict__ 
 }
 
 // ------------------------------------------------------------------------------------------------
+// camera -> world epilogue: the step the renderer applies to every ray after
+// camera_create_ray.  origin' = M (origin, 1), dir' = M3x3 dir with M a row-major 3x4 matrix; weight and tries
+// pass through.  One 32-byte record in, one out (in place allowed): HBM-bound, 64 bytes per ray.
+// Arithmetic (the contract the oracle restates): each output component is one fma chain, innermost term first,
+//   o'_r = fma(m[r][0], ox, fma(m[r][1], oy, fma(m[r][2], oz, m[r][3])))
+//   d'_r = fma(m[r][0], dx, fma(m[r][1], dy, m[r][2] * dz))
+// ------------------------------------------------------------------------------------------------
+struct Xform { float m[12]; };
+
+__device__ __forceinline__ void load_ray(const RayRecord* __restrict__ rays, uint64_t idx, float4* o, float4* d) {
+    asm volatile("ld.global.cs.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(o->x), "=f"(o->y), "=f"(o->z), "=f"(o->w), "=f"(d->x), "=f"(d->y), "=f"(d->z), "=f"(d->w)
+                 : "l"(rays + idx));
+}
+
+__global__ void __launch_bounds__(256)
+transform_rays_kernel(const __grid_constant__ Xform X, const RayRecord* __restrict__ in, uint64_t n, RayRecord* __restrict__ out) {
+    const float* m = X.m;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        float4 o, d;
+        load_ray(in, i, &o, &d);
+        float4 oo, dd;
+        oo.x = __fmaf_rn(m[0], o.x, __fmaf_rn(m[1], o.y, __fmaf_rn(m[2], o.z, m[3])));
+        oo.y = __fmaf_rn(m[4], o.x, __fmaf_rn(m[5], o.y, __fmaf_rn(m[6], o.z, m[7])));
+        oo.z = __fmaf_rn(m[8], o.x, __fmaf_rn(m[9], o.y, __fmaf_rn(m[10], o.z, m[11])));
+        oo.w = o.w;
+        dd.x = __fmaf_rn(m[0], d.x, __fmaf_rn(m[1], d.y, __fmul_rn(m[2], d.z)));
+        dd.y = __fmaf_rn(m[4], d.x, __fmaf_rn(m[5], d.y, __fmul_rn(m[6], d.z)));
+        dd.z = __fmaf_rn(m[8], d.x, __fmaf_rn(m[9], d.y, __fmul_rn(m[10], d.z)));
+        dd.w = d.w;
+        store_ray(out, i, oo, dd);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // fp32 peak probe: 8 independent FFMA chains per thread
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) ffma_peak_kernel(float* out, int iters, float a, float b) {
@@ -296,8 +332,11 @@ static cudaError_t launch_variant(const CameraState& cam, int mode, const float4
     if (mode == 1 && kModel == 1) {  // guarded fast path + exact re-run of the undecided samples
         cudaError_t e = cudaMemsetAsync(ws.counters, 0, 4 * sizeof(unsigned long long), st);
         if (e != cudaSuccess) return e;
-        // ZOICB_POOL=1 selects the scalar (one ray per lane) pool kernel, kept for A/B measurements
-        static const bool scalar_pool = [] { const char* v = getenv("ZOICB_POOL"); return v && v[0] == '1'; }();
+        // Two pool kernels: the packed one (two rays per lane, FFMA2) is the faster of the two except for cameras
+        // whose attempts mostly die inside stage A (in-pass re-sampling flavour), where the scalar kernel's per-lane
+        // early exit still wins (profiles/r01_ab_pool2.txt).  ZOICB_POOL=1 / 2 forces the scalar / packed kernel.
+        static const int force_pool = [] { const char* v = getenv("ZOICB_POOL"); return v ? atoi(v) : 0; }();
+        const bool scalar_pool = force_pool == 1 || (force_pool != 2 && cam.lens.inner_retry != 0);
         e = scalar_pool ? launch_kolb_pool(cam, samples, n, first_index, seed, rays, stats, st, ws, smem, launches)
                         : launch_kolb_pool2(cam, samples, n, first_index, seed, rays, stats, st, ws, smem, launches);
         if (e != cudaSuccess) return e;
@@ -353,6 +392,15 @@ cudaError_t launch_synth(uint32_t W, uint32_t H, uint32_t spp, uint64_t seed, ui
                          float4* out, cudaStream_t st, int* launches) {
     if (n == 0) return cudaSuccess;
     synth_samples_kernel<<<grid_for(n, 256, 8), 256, 0, st>>>(W, H, spp, seed, first_index, n, out);
+    if (launches) *launches += 1;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_transform(const float* m3x4, const RayRecord* in, uint64_t n, RayRecord* out, cudaStream_t st, int* launches) {
+    if (n == 0) return cudaSuccess;
+    Xform X;
+    for (int i = 0; i < 12; ++i) X.m[i] = m3x4[i];
+    transform_rays_kernel<<<grid_for(n, 256, 8), 256, 0, st>>>(X, in, n, out);
     if (launches) *launches += 1;
     return cudaGetLastError();
 }
