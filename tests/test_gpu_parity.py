@@ -407,10 +407,10 @@ def test_camera_to_world_epilogue_matches_the_contract(port):
         torch.cuda.synchronize()
         assert bits_equal(got.cpu().numpy(), want)
         assert bits_equal(got.cpu().numpy()[:, 3], host[:, 3]) and bits_equal(got.cpu().numpy()[:, 7], host[:, 7])
-    # rigid motion keeps directions unit length
+    # rigid motion keeps directions unit length (to the fp32 rounding of the matrix and of the directions themselves)
     g = cam.transform_rays(rays, rigid).cpu().numpy()
     live = host[:, 3] != 0
-    assert np.abs(np.linalg.norm(g[live, 4:7].astype(np.float64), axis=1) - 1.0).max() < 1e-6
+    assert np.abs(np.linalg.norm(g[live, 4:7].astype(np.float64), axis=1) - 1.0).max() < 5e-6
     ident = np.eye(3, 4, dtype=np.float32)
     same = cam.transform_rays(rays, ident).cpu().numpy()
     # identity: fma(1, x, fma(0, y, fma(0, z, 0))) = x exactly (also for -0.0 + 0.0 = +0.0: compare values)

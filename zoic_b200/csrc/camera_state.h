@@ -11,6 +11,7 @@ namespace zoicb {
 constexpr int kMaxElements = 24;
 constexpr int kLutSize = 32;
 constexpr int kMaxBokehRows = 5120;  // row CDF + row indices are staged in 40 KB of shared memory
+constexpr int kBokehGuidePad = 4;   // guide tables hold n + 4 entries (k = 0 .. n + 3)
 constexpr int kMaxTries = 25;  // reference src/zoic.cpp:1767
 
 // One refracting surface, rear element (nearest the sensor) first.  Everything the march needs per
@@ -73,6 +74,11 @@ struct BokehTables {
     const int32_t* row_indices;  // [h]
     const float* cdf_column;     // [h*w], rows in ORIGINAL row order (indexed by actual row * w)
     const uint16_t* rel_column;  // [h*w], columnIndices[c] - row*w
+    // guide ("cutpoint") tables of the two inverse-CDF searches: guide[k] = upper_bound(cdf, fl(k / G)) for
+    // k <= G, = n beyond (G = n = table length; kBokehGuidePad extra entries), so that the answer for u lies in
+    // [guide[floor(u G) - 2], guide[floor(u G) + 3]] and the search only visits a handful of entries
+    const uint16_t* row_guide;   // [h + kBokehGuidePad]
+    const uint16_t* col_guide;   // [h * (w + kBokehGuidePad)], by actual row like cdf_column
     int32_t w, h;
     int32_t valid;
     int32_t pad;

@@ -48,6 +48,8 @@ struct zoicb_ctx {
     int32_t* d_row_idx = nullptr;
     float* d_cdf_col = nullptr;
     uint16_t* d_rel_col = nullptr;
+    uint16_t* d_row_guide = nullptr;
+    uint16_t* d_col_guide = nullptr;
     DeviceStats* d_stats = nullptr;
     // guarded-mode scratch, one per stream the caller uses (stream order serialises reuse)
     std::vector<float> base_guards;
@@ -124,6 +126,7 @@ void free_ctx(zoicb_ctx* c) {
     cudaSetDevice(c->device);
     for (auto& kv : c->workspaces) { cudaFree(kv.second.counters); cudaFree(kv.second.queue); }
     cudaFree(c->d_cdf_row); cudaFree(c->d_row_idx); cudaFree(c->d_cdf_col); cudaFree(c->d_rel_col);
+    cudaFree(c->d_row_guide); cudaFree(c->d_col_guide);
     cudaFree(c->d_stats);
     for (int s = 0; s < zoicb_ctx::kSlots; ++s) {
         if (c->streams[s]) cudaStreamDestroy(c->streams[s]);
@@ -194,10 +197,15 @@ zoicb_status zoicb_create(const zoicb_params* params, const float* rgb, int widt
         cudaMemcpy(c->d_cdf_row, hb.cdf_row.data(), hb.h * sizeof(float), cudaMemcpyHostToDevice);
         cudaMemcpy(c->d_row_idx, hb.row_indices.data(), hb.h * sizeof(int32_t), cudaMemcpyHostToDevice);
         cudaMemcpy(c->d_cdf_col, hb.cdf_column.data(), np * sizeof(float), cudaMemcpyHostToDevice);
+        if ((e = cudaMalloc(&c->d_row_guide, hb.row_guide.size() * sizeof(uint16_t))) != cudaSuccess) return bail(e, "cudaMalloc");
+        if ((e = cudaMalloc(&c->d_col_guide, hb.col_guide.size() * sizeof(uint16_t))) != cudaSuccess) return bail(e, "cudaMalloc");
+        cudaMemcpy(c->d_row_guide, hb.row_guide.data(), hb.row_guide.size() * sizeof(uint16_t), cudaMemcpyHostToDevice);
+        cudaMemcpy(c->d_col_guide, hb.col_guide.data(), hb.col_guide.size() * sizeof(uint16_t), cudaMemcpyHostToDevice);
         if ((e = cudaMemcpy(c->d_rel_col, rel.data(), np * sizeof(uint16_t), cudaMemcpyHostToDevice)) != cudaSuccess)
             return bail(e, "cudaMemcpy(bokeh tables)");
         BokehTables& bt = c->host.state.bokeh;
         bt.cdf_row = c->d_cdf_row; bt.row_indices = c->d_row_idx; bt.cdf_column = c->d_cdf_col; bt.rel_column = c->d_rel_col;
+        bt.row_guide = c->d_row_guide; bt.col_guide = c->d_col_guide;
         bt.w = hb.w; bt.h = hb.h; bt.valid = 1;
     }
     *out = c;

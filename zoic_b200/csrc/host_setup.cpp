@@ -427,6 +427,21 @@ zoicb_status build_bokeh(const float* rgb, int w, int h, int nch, HostBokeh* out
             out->cdf_column[i] = run;
         }
     }
+    // guide tables for the device-side searches (camera_state.h): they only narrow the range the search visits,
+    // the result stays std::upper_bound's
+    auto guide = [](const float* cdf, int n, uint16_t* g) {
+        int pos = 0;
+        for (int k = 0; k < n + kBokehGuidePad; ++k) {
+            if (k > n) { g[k] = (uint16_t)n; continue; }
+            const float t = (float)k / (float)n;
+            while (pos < n && !(t < cdf[pos])) ++pos;   // first index whose value is greater than t; t grows with k
+            g[k] = (uint16_t)pos;
+        }
+    };
+    out->row_guide.resize(h + kBokehGuidePad);
+    guide(out->cdf_row.data(), h, out->row_guide.data());
+    out->col_guide.resize((size_t)h * (w + kBokehGuidePad));
+    for (int r = 0; r < h; ++r) guide(out->cdf_column.data() + (size_t)r * w, w, out->col_guide.data() + (size_t)r * (w + kBokehGuidePad));
     return ZOICB_OK;
 }
 

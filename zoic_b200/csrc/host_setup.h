@@ -15,6 +15,7 @@ struct HostBokeh {
     int w = 0, h = 0;
     std::vector<float> cdf_row, cdf_column;
     std::vector<int32_t> row_indices, column_indices;
+    std::vector<uint16_t> row_guide, col_guide;   // search accelerators for the device (camera_state.h); not part of parity
     bool valid() const { return w > 0 && h > 0; }
 };
 

@@ -22,15 +22,26 @@ __device__ __forceinline__ void store_ray(RayRecord* __restrict__ rays, uint64_t
 // ------------------------------------------------------------------------------------------------
 // image-based aperture sampling (reference imageData::bokehSample, src/zoic.cpp:420-485)
 // ------------------------------------------------------------------------------------------------
-// std::upper_bound over a[0..n): first index whose value is greater than u, with libstdc++'s probe sequence
-// (first/len halving).  The loop runs a warp-uniform number of rounds (bit length of n) with predicated
-// updates instead of a per-lane trip count: no divergence, and -- the reason it is written this way -- no
-// lane leaves the loop early.  (With a data-dependent trip count ptxas 12.9 let the early lanes run ahead and
-// re-use the uniform registers that hold the table pointers while the late lanes were still reading them.)
-template <typename Load>
-__device__ __forceinline__ int upper_bound_rounds(int n, float u, Load load) {
+// std::upper_bound over a[0..n): first index whose value is greater than u.  The guide table (camera_state.h)
+// brackets the answer: with k = floor(u n) -- computed in fp32, so off by at most one -- the thresholds
+// fl((k-2)/n) <= u < fl((k+3)/n) hold with room for every rounding involved, hence
+//   guide[k-2] <= answer <= guide[k+3],
+// and the libstdc++ first/len halving runs over that handful of entries only (a uniform u meets about five of
+// them on average, whatever the image).  u >= 1 lands on the padded tail (= n); NaN and negative u take the whole
+// range.  The loop runs a warp-uniform number of rounds with predicated updates: no divergence, and -- the reason
+// it is written this way -- no lane leaves the loop early.  (With a data-dependent trip count ptxas 12.9 let the
+// early lanes run ahead and re-use the uniform registers that hold the table pointers while the late lanes were
+// still reading them.)
+template <typename Load, typename Guide>
+__device__ __forceinline__ int upper_bound_guided(int n, float u, Load load, Guide guide) {
     int first = 0, len = n;
-    const int rounds = 32 - __clz(n);  // len halves every round: n -> 0 in at most bit_length(n) rounds
+    if (u >= 0.0f) {
+        const float f = u * (float)n;
+        const int k = f >= (float)n ? n : (int)f;
+        first = guide(k >= 2 ? k - 2 : 0);
+        len = guide(k + 3) - first;
+    }
+    const int rounds = 32 - __clz(__reduce_max_sync(__activemask(), (unsigned)len));
     for (int it = 0; it < rounds; ++it) {
         const int half = len >> 1;
         const int mid = first + half;
@@ -51,17 +62,20 @@ extern __shared__ float s_rows[];
 struct BokehView {
     const float* cdf_col;     // global
     const uint16_t* rel_col;
+    const uint16_t* row_guide;
+    const uint16_t* col_guide;
     int w, h;
 };
 
 __device__ __forceinline__ void bokeh_sample(const BokehView& b, float u_row, float u_col, float* dx, float* dy) {
-    int r = upper_bound_rounds(b.h, u_row, [&](int i) { return s_rows[i]; });
+    int r = upper_bound_guided(b.h, u_row, [&](int i) { return s_rows[i]; }, [&](int k) { return (int)__ldg(b.row_guide + k); });
     if (r >= b.h) r = b.h - 1;
     const int row = __float_as_int(s_rows[b.h + r]);
     const int rrow = row - ((b.w - 1) / 2);  // centred with the WIDTH (:441)
     const int start = row * b.w;
     const float* __restrict__ col = b.cdf_col + start;
-    int c = upper_bound_rounds(b.w, u_col, [&](int i) { return __ldg(col + i); });
+    const uint16_t* __restrict__ cg = b.col_guide + row * (b.w + kBokehGuidePad);
+    int c = upper_bound_guided(b.w, u_col, [&](int i) { return __ldg(col + i); }, [&](int k) { return (int)__ldg(cg + k); });
     if (c >= b.w) c = b.w - 1;
     const int rel = (int)__ldg(b.rel_col + start + c);
     const int rcol = rel - ((b.h - 1) / 2);  // centred with the HEIGHT (:466)
@@ -91,6 +105,8 @@ __device__ __forceinline__ BokehView stage_bokeh(const CameraState& cam) {
     b.w = cam.bokeh.w; b.h = cam.bokeh.h;
     b.cdf_col = cam.bokeh.cdf_column;
     b.rel_col = cam.bokeh.rel_column;
+    b.row_guide = cam.bokeh.row_guide;
+    b.col_guide = cam.bokeh.col_guide;
     for (int i = threadIdx.x; i < b.h; i += blockDim.x) {
         s_rows[i] = cam.bokeh.cdf_row[i];
         s_rows[b.h + i] = __int_as_float(cam.bokeh.row_indices[i]);
