@@ -15,19 +15,20 @@ namespace zoicb {
 
 // CTA shape and pool size per kernel flavour (A/B on the GPU, profiles/r01_ab_pool2.txt).  Slots per warp: a pass
 // takes 64 slots from stack A or B, or 32 free slots for new samples; with 160 slots (nA <= 63 and nB <= 63 leave
-// at least 34 free) one of the three is always possible (pigeonhole); 128 slots buy a fifth resident CTA per SM at
-// the price of an occasional partial pass.  The in-pass re-sampling flavour needs more registers (4 CTAs).
+// at least 34 free) one of the three is always possible (pigeonhole); 128 slots buy more resident warps per SM
+// (7 CTAs x 3 warps) at the price of an occasional partial pass.  The in-pass re-sampling flavour needs more
+// registers (5 CTAs x 3 warps, 160 slots).
 #ifndef ZOICB_POOL2_WARPS
-#define ZOICB_POOL2_WARPS 4
+#define ZOICB_POOL2_WARPS 3
 #endif
 #ifndef ZOICB_POOL2_CTAS
-#define ZOICB_POOL2_CTAS 5
+#define ZOICB_POOL2_CTAS 7
 #endif
 #ifndef ZOICB_POOL2_SLOTS
 #define ZOICB_POOL2_SLOTS 128
 #endif
 #ifndef ZOICB_POOL2_CTAS_INNER
-#define ZOICB_POOL2_CTAS_INNER 4
+#define ZOICB_POOL2_CTAS_INNER 5
 #endif
 #ifndef ZOICB_POOL2_SLOTS_INNER
 #define ZOICB_POOL2_SLOTS_INNER 160
