@@ -164,6 +164,8 @@ def _check_guarded(kw, port, n=400_000, seed=21, image=None):
     o2, d2, st2 = ref.generate(s, seed=seed, first_index=999, nthreads=8)
     res = compare_rays(o, d, o2, d2, tol=1e-5)
     assert res["path_flips"] == 0 and res["out_of_tol"] == 0, res
+    # zero-weight rays too must be well-formed records (film point + optical axis, or the exact path's last attempt)
+    assert np.isfinite(o).all() and np.isfinite(d).all()
     assert st["rays"] == n and st["attempts"] == st2["attempts"] and st["element_visits"] == st2["element_visits"]
     assert st["success"] == st2["success"] and st["vignetted"] == st2["vignetted"]
     assert st["total_internal_reflection"] == st2["tir"]
@@ -421,3 +423,18 @@ def test_camera_to_world_epilogue_matches_the_contract(port):
     assert bits_equal(inplace.cpu().numpy(), port.transform_rays(host, general))
     cam.transform_rays(rays[:0], general)
     cam.close()
+
+
+@pytest.mark.parametrize("pool", ["1", "2"])
+def test_both_pool_kernels_on_every_lens(pool):
+    """The host picks the scalar or the packed pool kernel per camera; ZOICB_POOL=1 / 2 forces one of them (read once
+    per process), so the all-lenses and bokeh parity tests run again in a child process for each."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, ZOICB_POOL=pool)
+    here = os.path.dirname(os.path.abspath(__file__))
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(here, "test_gpu_parity.py"), "-q", "-x", "-m", "gpu", "-k",
+                        "guarded_kolb_all_lenses or guarded_kolb_no_lut_and_bokeh or guarded_kolb_bokeh_image_sizes or "
+                        "large_batch_spans_many_chunks"], env=env, capture_output=True, text=True, cwd=os.path.dirname(here))
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]

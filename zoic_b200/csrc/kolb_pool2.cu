@@ -237,10 +237,14 @@ kolb_pool2_kernel(const __grid_constant__ CameraState cam, const float4* __restr
     // a finished sample: counters and the output record.  A sample that ran out of retries gets weight 0 and --
     // its half-traced state being meaningless in the reference too -- the film point as
     // origin and the optical axis as direction.
-    auto emit = [&](uint32_t idx, unsigned packed, float ox, float oy, float oz, float ux, float uy, float uz) {
+    auto emit = [&](int slot, uint32_t idx, unsigned packed, float ox, float oy, float oz, float ux, float uy, float uz) {
         const unsigned tries = pk2_tries(packed);
         float weight = 1.0f;
-        if (tries > (unsigned)kMaxTries) { weight = 0.0f; ls.vignetted++; ux = 0.0f; uy = 0.0f; uz = 1.0f; }
+        if (tries > (unsigned)kMaxTries) {   // the marched state of a stopped ray is dead (NaN): film point, optical axis
+            const float4 f = P.film[slot];
+            weight = 0.0f; ls.vignetted++;
+            ox = f.x; oy = f.y; oz = L.origin_shift; ux = 0.0f; uy = 0.0f; uz = 1.0f;
+        }
         else ls.success++;
         weight *= cam.weight_scale;
         store_ray(rays, idx, make_float4(-ox, -oy, -oz, weight), make_float4(-ux, -uy, -uz, (float)tries));
@@ -352,7 +356,7 @@ kolb_pool2_kernel(const __grid_constant__ CameraState cam, const float4* __restr
                 und[h] = act && rc == kUndecided;
                 if (again[h]) P.misc[h ? slot1 : slot0].w = __uint_as_float(packed);
                 if (done[h])
-                    emit(h ? idx1 : idx0, packed, half_of(r.ox, h), half_of(r.oy, h), half_of(r.oz, h), half_of(r.ux, h),
+                    emit(h ? slot1 : slot0, h ? idx1 : idx0, packed, half_of(r.ox, h), half_of(r.oy, h), half_of(r.oz, h), half_of(r.ux, h),
                          half_of(r.uy, h), half_of(r.uz, h));
             }
             enqueue2(und[0], idx0, und[1], idx1);
@@ -458,7 +462,7 @@ kolb_pool2_kernel(const __grid_constant__ CameraState cam, const float4* __restr
                     P.misc[slot].w = __uint_as_float(packed);
                 }
                 if (done[h])
-                    emit(idx, packed, half_of(r.ox, h), half_of(r.oy, h), half_of(r.oz, h), half_of(r.ux, h), half_of(r.uy, h),
+                    emit(slot, idx, packed, half_of(r.ox, h), half_of(r.oy, h), half_of(r.oz, h), half_of(r.ux, h), half_of(r.uy, h),
                          half_of(r.uz, h));
             }
             enqueue2(und[0], idx0, und[1], idx1);
