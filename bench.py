@@ -166,7 +166,7 @@ def main():
     ap.add_argument("--mode", default="default", choices=["default", "exact", "guarded"])
     ap.add_argument("--samples", type=int, default=0, help="override samples per GPU per step (debug)")
     ap.add_argument("--spp", type=int, default=0, help="override samples per pixel (profiling: a small batch that still covers the whole film)")
-    ap.add_argument("--e2e-samples", type=int, default=1 << 26)
+    ap.add_argument("--e2e-samples", type=int, default=1 << 27)
     ap.add_argument("--cpu-samples", type=int, default=1 << 22, help="CPU baseline sample size (all cores)")
     ap.add_argument("--gather", action="store_true", help="N > 1: also time generation + NCCL all-gather of a 2^26-ray tile")
     ap.add_argument("--no-cpu", action="store_true")

@@ -4,6 +4,7 @@
 #include <atomic>
 #include <map>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -269,7 +270,11 @@ zoicb_status zoicb_generate_host(zoicb_ctx* ctx, const float* h_samples, uint64_
     ZCUDA(cudaSetDevice(ctx->device), "cudaSetDevice");
     constexpr int K = zoicb_ctx::kSlots;
     if (!ctx->chunk) {
-        ctx->chunk = 1ull << 22;  // 4 Mi samples: 64 MiB up, 128 MiB down per slot
+        // samples per pipeline slot: 2 Mi by default (32 MiB up, 64 MiB down; small enough that the un-overlapped first
+        // upload and last download do not show, profiles/r01_ab_pool2.txt); ZOICB_HOST_CHUNK_LOG2 overrides (A/B)
+        const char* cl = getenv("ZOICB_HOST_CHUNK_LOG2");
+        const int lg = cl ? atoi(cl) : 21;
+        ctx->chunk = 1ull << (lg >= 16 && lg <= 26 ? lg : 21);
         for (int s = 0; s < K; ++s) {
             ZCUDA(cudaStreamCreateWithFlags(&ctx->streams[s], cudaStreamNonBlocking), "cudaStreamCreate");
             ZCUDA(cudaMalloc(&ctx->d_in[s], ctx->chunk * sizeof(float4)), "cudaMalloc(staging)");
