@@ -12,6 +12,7 @@
  *   zoicb_get_stats     the counters printed by node_finish      src/zoic.cpp:1729-1732
  *   zoicb_destroy       node_finish                              src/zoic.cpp:1723-1749
  *   zoicb_transform_rays  (the renderer's camera-to-world step after camera_create_ray; nothing in zoic)
+ *   zoicb_write_draw_file writeToFile + the DRAW_ONLY ray dumps  src/zoic.cpp:1240-1293, 1121-1128, 1146-1153
  *   zoicb_params        the 14 node parameters                   src/zoic.cpp:1547-1562
  * The Arnold-shaped per-sample surface (NodeLoader + the six node callbacks, src/zoic.cpp:1999-2007)
  * is exported by the same library from zoic_b200/csrc/arnold_adapter.cpp on top of these calls.
@@ -169,6 +170,17 @@ ZOICB_API zoicb_status zoicb_generate_one(zoicb_ctx* ctx, const float* sample, u
  * Arithmetic: one fma chain per component, innermost term first (zoic_b200/csrc/kernels.cu). */
 ZOICB_API zoicb_status zoicb_transform_rays(zoicb_ctx* ctx, const zoicb_ray* d_rays, uint64_t n, const float* m3x4,
                                             zoicb_ray* d_out, void* stream);
+
+/* draw.zoic writer: the file the reference's -D_DRAW build leaves for src/draw.py
+ * (writeToFile, src/zoic.cpp:1240-1293, and the DRAW_ONLY blocks of traceThroughLensElements :1121-1128,
+ * :1146-1153): "LENSMODEL{KOLB}", the lens cross-section header, then "RAYS{...}" with the (z, y) path of every
+ * attempt of every given sample through the element stack, traced on the GPU with the exact arithmetic and the
+ * draw build's conventions (film point x = 0, direction x = 0).  The reference draws one sample in 100 000; here
+ * the caller picks them: h_samples is n x (sx, sy, lensx, lensy) in HOST memory; sample i has global index
+ * h_indices[i], or first_index + i when h_indices is NULL (the index selects its retry stream).  Raytraced lens
+ * model only; at most 65536 samples. */
+ZOICB_API zoicb_status zoicb_write_draw_file(zoicb_ctx* ctx, const char* path, const float* h_samples, uint32_t n,
+                                             const uint64_t* h_indices, uint64_t first_index, uint64_t rng_seed);
 
 /* Synthetic camera samples for benchmarks and parity tests: sample index i is
  * pixel-major / spp-minor over a W x H image, four 24-bit uniforms from a counter hash of (seed, i). */

@@ -438,3 +438,30 @@ def test_both_pool_kernels_on_every_lens(pool):
                         "guarded_kolb_all_lenses or guarded_kolb_no_lut_and_bokeh or guarded_kolb_bokeh_image_sizes or "
                         "large_batch_spans_many_chunks"], env=env, capture_output=True, text=True, cwd=os.path.dirname(here))
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("case", ["dg_f28_focus23", "dg_nolut", "fisheye"])
+def test_draw_file_matches_the_reference_draw_build(case, tmp_path):
+    """zoicb_write_draw_file against draw.zoic files written by the -D_DRAW build of the unmodified
+    reference (tests/golden/draw_rays_*.txt, tools/make_golden_draw.py) for the samples that build drew: byte for byte,
+    header and every attempt's (z, y) path."""
+    import os
+    from zoic_b200 import ZoicCamera
+    from zoic_b200.workloads import lens_path
+    sys_path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tools")
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden_draw", os.path.join(sys_path, "make_golden_draw.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    kw = dict(mg.CASES[case])
+    kw["lensDataPath"] = lens_path(kw["lensDataPath"])
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    data = np.load(os.path.join(gold, "draw_rays_%s.npz" % case))
+    want = open(os.path.join(gold, "draw_rays_%s.txt" % case)).read()
+    cam = ZoicCamera(lensModel=1, **kw)
+    out = tmp_path / "draw.zoic"
+    cam.write_draw_file(str(out), data["samples"], seed=int(data["seed"]), indices=data["index"])
+    got = open(out).read()
+    cam.close()
+    assert got.split("RAYS{")[0] == want.split("RAYS{")[0]          # header
+    assert got == want

@@ -8,6 +8,7 @@ of (sx, sy, lensx, lensy) samples; `stats()` returns the counters node_finish pr
 torch is used only to own device memory and streams; the data path is libzoicb's CUDA kernels.
 """
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -137,6 +138,15 @@ class ZoicCamera:
             out = np.empty((n, 8), np.float32)
         capi.check(self.lib.zoicb_generate_host(self.ctx, ptr(samples), n, first_index, seed, ptr(out)))
         return out
+
+    def write_draw_file(self, path, samples, seed=0, first_index=0, indices=None):
+        """draw.zoic for the reference's src/draw.py: header + the (z, y) paths of every attempt of
+        the given samples ([n, 4] host array), traced on the GPU with the draw build's conventions.  `indices`
+        (optional, [n] uint64) are the samples' global indices (retry streams); default first_index + i."""
+        s = np.ascontiguousarray(samples, dtype=np.float32).reshape(-1, 4)
+        idx = None if indices is None else np.ascontiguousarray(indices, dtype=np.uint64)
+        capi.check(self.lib.zoicb_write_draw_file(self.ctx, os.fsencode(path), s.ctypes.data, s.shape[0],
+                                                  None if idx is None else idx.ctypes.data, first_index, seed))
 
     def transform_rays(self, rays, camera_to_world, out=None, stream=None):
         """Camera -> world epilogue: rays [n, 8] on the device, camera_to_world a 3x4 row-major

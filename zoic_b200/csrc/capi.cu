@@ -3,6 +3,7 @@
 
 #include <atomic>
 #include <map>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -362,6 +363,80 @@ zoicb_status zoicb_generate_one(zoicb_ctx* ctx, const float* sample, uint64_t sa
     ZCUDA(cudaMemcpyAsync(&r.h[2], &r.d[2], 2 * sizeof(float4), cudaMemcpyDeviceToHost, r.stream), "D2H");
     ZCUDA(cudaStreamSynchronize(r.stream), "cudaStreamSynchronize");
     std::memcpy(ray, &r.h[2], sizeof(zoicb_ray));
+    return ZOICB_OK;
+}
+
+zoicb_status zoicb_write_draw_file(zoicb_ctx* ctx, const char* path, const float* h_samples, uint32_t n,
+                                   const uint64_t* h_indices, uint64_t first_index, uint64_t rng_seed) {
+    if (!ctx || !path) return fail(ZOICB_ERR_INVALID_ARGUMENT, "zoicb_write_draw_file: null argument");
+    if (n && !h_samples) return fail(ZOICB_ERR_INVALID_ARGUMENT, "zoicb_write_draw_file: null samples");
+    if (ctx->host.state.lens_model != ZOICB_RAYTRACED)
+        return fail(ZOICB_ERR_UNSUPPORTED, "zoicb_write_draw_file: raytraced lens model only");
+    if (n > 65536) return fail(ZOICB_ERR_INVALID_ARGUMENT, "zoicb_write_draw_file: at most 65536 samples");
+    const zoicb_constants& C = ctx->host.constants;
+    const uint32_t cap = (uint32_t)(kMaxTries + 2) * (uint32_t)(C.lensCount + 1);
+    std::vector<float4> quads((size_t)n * cap);
+    std::vector<uint8_t> kinds((size_t)n * cap);
+    std::vector<uint32_t> counts(n);
+    if (n) {
+        ZCUDA(cudaSetDevice(ctx->device), "cudaSetDevice");
+        float4 *d_s = nullptr, *d_q = nullptr;
+        uint8_t* d_k = nullptr;
+        uint32_t* d_c = nullptr;
+        unsigned long long* d_i = nullptr;
+        cudaError_t e = cudaSuccess;
+        int launches = 0;
+        do {
+            if ((e = cudaMalloc(&d_s, n * sizeof(float4))) != cudaSuccess) break;
+            if ((e = cudaMalloc(&d_q, quads.size() * sizeof(float4))) != cudaSuccess) break;
+            if ((e = cudaMalloc(&d_k, kinds.size())) != cudaSuccess) break;
+            if ((e = cudaMalloc(&d_c, n * sizeof(uint32_t))) != cudaSuccess) break;
+            if ((e = cudaMemcpy(d_s, h_samples, n * sizeof(float4), cudaMemcpyHostToDevice)) != cudaSuccess) break;
+            if (h_indices) {
+                if ((e = cudaMalloc(&d_i, n * sizeof(unsigned long long))) != cudaSuccess) break;
+                if ((e = cudaMemcpy(d_i, h_indices, n * sizeof(unsigned long long), cudaMemcpyHostToDevice)) != cudaSuccess) break;
+            }
+            if ((e = launch_draw_paths(ctx->host.state, d_s, n, d_i, first_index, rng_seed, d_q, d_k, d_c, cap, nullptr, &launches)) != cudaSuccess) break;
+            if ((e = cudaMemcpy(quads.data(), d_q, quads.size() * sizeof(float4), cudaMemcpyDeviceToHost)) != cudaSuccess) break;
+            if ((e = cudaMemcpy(kinds.data(), d_k, kinds.size(), cudaMemcpyDeviceToHost)) != cudaSuccess) break;
+            e = cudaMemcpy(counts.data(), d_c, n * sizeof(uint32_t), cudaMemcpyDeviceToHost);
+        } while (0);
+        cudaFree(d_s); cudaFree(d_q); cudaFree(d_k); cudaFree(d_c); cudaFree(d_i);
+        count_launches(launches);
+        if (e != cudaSuccess) return cuda_fail(e, "zoicb_write_draw_file");
+    }
+    FILE* f = std::fopen(path, "w");
+    if (!f) return fail(ZOICB_ERR_INVALID_ARGUMENT, std::string("zoicb_write_draw_file: cannot open ") + path);
+    // header: src/zoic.cpp:1618 and writeToFile :1240-1293 (std::fixed << std::setprecision(10) == "%.10f")
+    std::fprintf(f, "LENSMODEL{KOLB}\nLENSES{");
+    const double deg = (double)(180 / 3.14159265358979323846f);   // 180 / AI_PI is a float division
+    float max_ap = 0.0f;
+    for (int i = 0; i < C.lensCount; ++i) {
+        const double ang = std::asin(((double)C.aperture[i] * 0.5) / (double)C.curvature[i]) * deg;
+        std::fprintf(f, "%.10f %.10f %.10f ", (double)-C.center[i], (double)-C.curvature[i], ang);
+        if (C.aperture[i] > max_ap) max_ap = C.aperture[i];
+    }
+    std::fprintf(f, "}\nIOR{");
+    for (int i = 0; i < C.lensCount; ++i) std::fprintf(f, "%.10f ", (double)C.ior[i]);
+    std::fprintf(f, "}\nAPERTUREELEMENT{%d}\n", C.apertureElement);
+    std::fprintf(f, "APERTUREDISTANCE{%.10f}\n", (double)-C.apertureDistance);
+    std::fprintf(f, "APERTURE{%.10f}\n", (double)C.userApertureRadius);
+    std::fprintf(f, "APERTUREMAX{%.10f}\n", (double)max_ap);
+    std::fprintf(f, "FOCUSDISTANCE{%.10f}\n", (double)-ctx->host.params.focalDistance);
+    std::fprintf(f, "IMAGEDISTANCE{%.10f}\n", (double)-C.originShift);
+    std::fprintf(f, "SENSORHEIGHT{%.10f}\nRAYS{", 1.7);
+    for (uint32_t i = 0; i < n; ++i) {
+        for (uint32_t k = 0; k < counts[i] && k < cap; ++k) {
+            const float4 q = quads[(size_t)i * cap + k];
+            if (kinds[(size_t)i * cap + k] == 0)   // :1121-1128
+                std::fprintf(f, "%.10f %.10f %.10f %.10f ", (double)-q.x, (double)-q.y, (double)-q.z, (double)-q.w);
+            else                                   // :1146-1153: float + float * -10000.0 evaluated in double
+                std::fprintf(f, "%.10f %.10f %.10f %.10f ", (double)-q.x, (double)-q.y, (double)q.x + (double)q.z * -10000.0,
+                             (double)q.y + (double)q.w * -10000.0);
+        }
+    }
+    std::fprintf(f, "}");
+    std::fclose(f);
     return ZOICB_OK;
 }
 

@@ -264,6 +264,55 @@ lut_trace_kernel(const __grid_constant__ LensState L, const float* __restrict__ 
 }
 
 // ------------------------------------------------------------------------------------------------
+// draw.zoic ray paths: what the reference's -D_DRAW build writes from inside
+// traceThroughLensElements (src/zoic.cpp:1121-1128, :1146-1153) for a drawn sample -- per surface whose rim test
+// passed, the ray origin and the hit point (z, y); after the last surface, the hit point and the exit direction --
+// for EVERY attempt of the sample, with the draw build's conventions (film point x = 0 :1859, direction x = 0
+// :1877/:1925/:1944).  One thread per sample, exact arithmetic; the host formats the numbers.
+// quads: per sample `cap` records of 4 floats; kinds: 0 = (o.z, o.y, hit.z, hit.y), 1 = (hit.z, hit.y, dir.z, dir.y).
+// ------------------------------------------------------------------------------------------------
+template <bool kImage, bool kLut>
+__global__ void __launch_bounds__(128)
+draw_paths_kernel(const __grid_constant__ CameraState cam, const float4* __restrict__ samples, uint32_t n,
+                  const unsigned long long* __restrict__ indices, uint64_t first_index, uint64_t seed, float4* __restrict__ quads, uint8_t* __restrict__ kinds, uint32_t* __restrict__ counts,
+                  uint32_t cap) {
+    BokehView bk;
+    if (kImage) bk = stage_bokeh(cam);
+    const LensState& L = cam.lens;
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    // all lanes run the (warp-uniform round count) table searches; lanes past the end work on sample n - 1 and store nothing
+    const bool live = i < n;
+    const float4 s = samples[live ? i : n - 1];
+    const KolbSampleState k = kolb_sample_setup<kLut, true>(L, 0.0f, s.y);   // origin.x = 0 before the LUT lookup
+    float4* q = quads + (size_t)(live ? i : 0) * cap;
+    uint8_t* kd = kinds + (size_t)(live ? i : 0) * cap;
+    uint32_t nq = 0;
+    const uint32_t j = live ? i : n - 1;
+    Xor128 rng = sample_stream(seed, indices ? (uint64_t)indices[j] : first_index + j);
+    float u = s.z, v = s.w;
+    for (int tries = 0;; ++tries) {
+        float lx, ly;
+        lens_sample<kImage>(bk, u, v, &lx, &ly);
+        Ray r;
+        r.o = vmake(k.fx, k.fy, L.origin_shift);
+        r.d = kolb_aim<kLut>(L, k, lx, ly, tries > 0);
+        r.d.x = 0.0f;
+        int rc = kPass;
+        for (int e = 0; e < L.count; ++e) {
+            const Vec3 o_old = r.o;
+            rc = exact_surface(L.e[e], r);
+            if (rc == kBlocked) break;   // missed the sphere or the rim: nothing is written for this surface
+            if (live && nq < cap) { q[nq] = make_float4(o_old.z, o_old.y, r.o.z, r.o.y); kd[nq] = 0; ++nq; }
+            if (rc == kTir) break;
+            if (e == L.count - 1 && live && nq < cap) { q[nq] = make_float4(r.o.z, r.o.y, r.d.z, r.d.y); kd[nq] = 1; ++nq; }
+        }
+        if (rc == kPass || tries > kMaxTries) break;
+        draw_pair(rng, &u, &v);
+    }
+    if (live) counts[i] = nq;
+}
+
+// ------------------------------------------------------------------------------------------------
 // camera -> world epilogue: the step the renderer applies to every ray after
 // camera_create_ray.  origin' = M (origin, 1), dir' = M3x3 dir with M a row-major 3x4 matrix; weight and tries
 // pass through.  One 32-byte record in, one out (in place allowed): HBM-bound, 64 bytes per ray.
@@ -392,6 +441,21 @@ cudaError_t launch_synth(uint32_t W, uint32_t H, uint32_t spp, uint64_t seed, ui
                          float4* out, cudaStream_t st, int* launches) {
     if (n == 0) return cudaSuccess;
     synth_samples_kernel<<<grid_for(n, 256, 8), 256, 0, st>>>(W, H, spp, seed, first_index, n, out);
+    if (launches) *launches += 1;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_draw_paths(const CameraState& cam, const float4* samples, uint32_t n, const unsigned long long* indices,
+                              uint64_t first_index, uint64_t seed,
+                              float4* quads, uint8_t* kinds, uint32_t* counts, uint32_t cap, cudaStream_t st, int* launches) {
+    if (n == 0) return cudaSuccess;
+    const unsigned grid = (n + 127) / 128;
+    const bool image = cam.use_image != 0, lut = cam.lens.use_lut != 0;
+    const size_t rows_smem = image ? (size_t)cam.bokeh.h * 8 : 0;
+#define ZD(I, U) draw_paths_kernel<I, U><<<grid, 128, rows_smem, st>>>(cam, samples, n, indices, first_index, seed, quads, kinds, counts, cap)
+    if (image) { if (lut) ZD(true, true); else ZD(true, false); }
+    else { if (lut) ZD(false, true); else ZD(false, false); }
+#undef ZD
     if (launches) *launches += 1;
     return cudaGetLastError();
 }

@@ -25,6 +25,9 @@ cudaError_t launch_synth(uint32_t W, uint32_t H, uint32_t spp, uint64_t seed, ui
                          float4* out, cudaStream_t st, int* launches);
 cudaError_t launch_lut_trace(const LensState& L, const float* d_film_x, int n_film, int per_film, const uint32_t* d_draws,
                              uint8_t* d_accept, cudaStream_t st, int* launches);
+cudaError_t launch_draw_paths(const CameraState& cam, const float4* samples, uint32_t n, const unsigned long long* indices,
+                              uint64_t first_index, uint64_t seed,
+                              float4* quads, uint8_t* kinds, uint32_t* counts, uint32_t cap, cudaStream_t st, int* launches);
 cudaError_t launch_transform(const float* m3x4, const RayRecord* in, uint64_t n, RayRecord* out, cudaStream_t st, int* launches);
 cudaError_t measure_fp32_peak(double* tflops, int* launches);
 
