@@ -1,5 +1,5 @@
 #!/bin/bash
-# scalar (ZOICB_POOL=1) against packed (ZOICB_POOL=2) pool kernel on the fisheye (config4, 8 spp) and on three
+# scalar (ZOICB_POOL=1) against packed (ZOICB_POOL=2) and packed + rim pre-test (ZOICB_POOL=3) pool kernel on the fisheye (config4, 8 spp) and on three
 # config-5 cameras with very different rejection rates; 265 M rays each
 run() { # name, python expression building the workload
 python - "$1" "$2" <<'PY'
@@ -26,7 +26,9 @@ print("%-8s %-26s %8.0f Mrays/s  %7.2f ms  attempts/ray %.2f visits/ray %.2f zer
     c["guardedSplit"], c["guardedInnerRetry"]))
 PY
 }
-for lens in config4 telephoto_f5.0.dat petzval_f1.25.dat tessar_f2.8.dat double_gauss_f2.0.dat; do
+for lens in ${LENSES:-config4 telephoto_f5.0.dat petzval_f1.25.dat tessar_f2.8.dat double_gauss_f2.0.dat}; do
   ZOICB_POOL=1 run scalar $lens
   ZOICB_POOL=2 run packed $lens
+  ZOICB_POOL=3 run pretest $lens
+  ZOICB_POOL=0 run auto $lens
 done

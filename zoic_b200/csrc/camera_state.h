@@ -51,7 +51,8 @@ struct LensState {
     float user_aperture_radius;
     int32_t split;            // guarded kernel: surfaces [0, split) run in stage A, [split, count) in stage B
     int32_t inner_retry;      // guarded kernel: rays stopped in stage A re-sample inside the pass (most attempts die there)
-    int32_t pad1, pad2;
+    int32_t pretest;          // guarded kernel: most attempts die at the first surface -> rim pre-test flavour (kolb_pool2.cu)
+    int32_t pad2;
     float lut_scale[kLutSize];  // boundingBox2d::getMaxScale() per LUT entry (src/zoic.cpp:503-517)
     float lut_cx[kLutSize];     // boundingBox2d::getCentroid().x per LUT entry
     Element e[kMaxElements];    // 16-byte aligned: the packed kernel reads an element as four 128-bit constant loads

@@ -327,9 +327,10 @@ void build_lut(LensState* L, zoicb_constants* C, LutTraceFn fn, void* user) {
 // stopped early (rear rim, stop) do not idle through the rest of the stack.  Where to cut depends on where
 // this camera's attempts die: trace a few thousand attempts on the host (exact arithmetic, samples spread over
 // the sensor), histogram the stopping surface and minimise a simple issue-slot model.
-int choose_split(const LensState& L, float sensor_w, float sensor_h, int* inner_retry) {
+int choose_split(const LensState& L, float sensor_w, float sensor_h, int* inner_retry, int* pretest) {
     const int n = L.count;
     *inner_retry = 0;
+    *pretest = 0;
     if (n < 2) return 1;
     std::vector<double> stop_at(n, 0.0);
     double pass = 0.0, total = 0.0;
@@ -367,6 +368,10 @@ int choose_split(const LensState& L, float sensor_w, float sensor_h, int* inner_
     double dead_a = 0.0;
     for (int i = 0; i < best; ++i) dead_a += stop_at[i];
     *inner_retry = dead_a / total > 0.5 ? 1 : 0;
+    // rim pre-test flavour of the packed kernel: wins on every camera whose attempts mostly die inside stage A
+    // (+5 % on the fisheye, whose attempts die on surfaces 0-5, to +12 % on the narrow-field lenses, where the first
+    // surface alone stops ~95 % of them; profiles/r01_ab_pool2.txt)
+    *pretest = *inner_retry;
     return best;
 }
 
@@ -537,7 +542,7 @@ zoicb_status build_camera(const zoicb_params& p, const float* rgb, int w, int h,
         C.aperture[i] = rows[i].aperture; C.center[i] = rows[i].center;
     }
     if (p.kolbSamplingLUT) build_lut(&L, &C, lut_fn, lut_user);  // :1691-1692
-    L.split = choose_split(L, p.sensorWidth, p.sensorHeight, &L.inner_retry);
+    L.split = choose_split(L, p.sensorWidth, p.sensorHeight, &L.inner_retry, &L.pretest);
     C.guardedSplit = L.split;
     C.guardedInnerRetry = L.inner_retry;
     return ZOICB_OK;

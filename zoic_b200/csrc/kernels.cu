@@ -381,13 +381,19 @@ static cudaError_t launch_variant(const CameraState& cam, int mode, const float4
     if (mode == 1 && kModel == 1) {  // guarded fast path + exact re-run of the undecided samples
         cudaError_t e = cudaMemsetAsync(ws.counters, 0, 4 * sizeof(unsigned long long), st);
         if (e != cudaSuccess) return e;
-        // Two pool kernels: the packed one (two rays per lane, FFMA2) is the faster of the two except for cameras
-        // whose attempts mostly die inside stage A (in-pass re-sampling flavour), where the scalar kernel's per-lane
-        // early exit still wins (profiles/r01_ab_pool2.txt).  ZOICB_POOL=1 / 2 forces the scalar / packed kernel.
+        // Three flavours of the pool kernel, chosen from the camera's calibration (host_setup.cpp: choose_split):
+        //   packed (two rays per lane, FFMA2)      -- most attempts survive the first surfaces (e.g. the double Gauss);
+        //   packed with a rim pre-test loop        -- most attempts die on the first surfaces (narrow-field lenses on a
+        //                                             wide sensor: 15-22 attempts per ray; the fisheye);
+        //   scalar with in-pass re-sampling        -- the previous kernel for those cameras, kept for A/B runs.
+        // ZOICB_POOL=1 / 2 / 3 forces scalar / packed / packed + pre-test (profiles/r01_ab_pool2.txt).
         static const int force_pool = [] { const char* v = getenv("ZOICB_POOL"); return v ? atoi(v) : 0; }();
-        const bool scalar_pool = force_pool == 1 || (force_pool != 2 && cam.lens.inner_retry != 0);
-        e = scalar_pool ? launch_kolb_pool(cam, samples, n, first_index, seed, rays, stats, st, ws, smem, launches)
-                        : launch_kolb_pool2(cam, samples, n, first_index, seed, rays, stats, st, ws, smem, launches);
+        CameraState c2 = cam;
+        if (force_pool == 3) c2.lens.pretest = 1;
+        if (force_pool == 1 || force_pool == 2) c2.lens.pretest = 0;
+        const bool scalar_pool = force_pool == 1 || (force_pool == 0 && c2.lens.inner_retry != 0 && c2.lens.pretest == 0);
+        e = scalar_pool ? launch_kolb_pool(c2, samples, n, first_index, seed, rays, stats, st, ws, smem, launches)
+                        : launch_kolb_pool2(c2, samples, n, first_index, seed, rays, stats, st, ws, smem, launches);
         if (e != cudaSuccess) return e;
         kolb_exact_persistent_kernel<kImage, kLut, true><<<(unsigned)sm_count() * 3, threads, smem, st>>>(
             cam, samples, 0, first_index, seed, rays, stats, ws.counters + 2, ws.queue, ws.counters + 1,

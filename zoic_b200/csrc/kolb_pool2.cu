@@ -38,9 +38,17 @@ namespace zoicb {
 #endif
 constexpr int kRollUnroll = ZOICB_POOL2_ROLLED > 0 ? ZOICB_POOL2_ROLLED : 1;
 constexpr int kWarps2 = ZOICB_POOL2_WARPS;
-template <bool kInner> struct PoolShape {
-    static constexpr int kSlots = kInner ? ZOICB_POOL2_SLOTS_INNER : ZOICB_POOL2_SLOTS;
-    static constexpr int kCtas = kInner ? ZOICB_POOL2_CTAS_INNER : ZOICB_POOL2_CTAS;
+// the rim pre-test loop goes round again while at least this many of the 64 rays of the pass still owe an attempt
+// (lower: fewer trips through the pool; higher: fewer idle lanes in the loop)
+#ifndef ZOICB_POOL2_PRE_KEEP
+#define ZOICB_POOL2_PRE_KEEP 48
+#endif
+constexpr int kPreKeepGoing = ZOICB_POOL2_PRE_KEEP;
+// kRoomy: the flavours that need more registers than 7 CTAs x 3 warps leave (97): in-pass re-sampling, image-based
+// aperture sampling (two table searches), run-time stage boundary
+template <bool kRoomy> struct PoolShape {
+    static constexpr int kSlots = kRoomy ? ZOICB_POOL2_SLOTS_INNER : ZOICB_POOL2_SLOTS;
+    static constexpr int kCtas = kRoomy ? ZOICB_POOL2_CTAS_INNER : ZOICB_POOL2_CTAS;
     static_assert(kSlots % 32 == 0 && kSlots >= 96 && kSlots <= 256, "slot ids are bytes; whole warps of slots");
 };
 
@@ -85,6 +93,33 @@ __device__ __forceinline__ float half_of(f2 v, int h) { return h ? hi(v) : lo(v)
 
 struct RayPair { f2 ox, oy, oz, ux, uy, uz; };
 
+// First half of the surface step for the two rays of a lane: intersection with the sphere the reference
+// intersects, hit point (returned in place of the origin), and the quantities of the rim / miss decision.
+__device__ __forceinline__ void surface_hit(const float4 q0, const float4 q1, const float4 q2, const float4 q3, f2& px, f2& py,
+                                            f2& pz, const f2 vx, const f2 vy, const f2 vz, f2* w, f2* margin, f2* guard,
+                                            f2* disc_out) {
+    const float e_center = q0.x, e_sgn = q0.w, e_rim2 = q1.x;
+    const float e_rim2_guard = q2.y, e_dt_guard = q2.z, e_vertex = q2.w, e_r2_corr = q3.x, e_vertex_m2r = q3.z;
+    const f2 dz = sub2(bc(e_vertex), pz);
+    const f2 m2 = sub2(bc(e_vertex_m2r), pz);                            // dz - 2R
+    const f2 Lz = sub2(bc(e_center), pz);
+    const f2 tca = fma2(Lz, vz, neg2(fma2(px, vx, mul2(py, vy))));
+    // C = |o - c|^2 - radius2 = dz (dz - 2R) + ox^2 + oy^2 + (R^2 - fl(R^2))
+    const f2 C = fma2(dz, m2, fma2(px, px, fma2(py, py, bc(e_r2_corr))));
+    const f2 disc = fma2(tca, tca, neg2(C));
+    const f2 s = mul2(bc(e_sgn), mk(approx_sqrt(fmaxf(lo(disc), 0.0f)), approx_sqrt(fmaxf(hi(disc), 0.0f))));
+    const f2 ts = mul2(tca, s);
+    const f2 den = sub2(tca, s);
+    const f2 sum = add2(tca, s);
+    const f2 conj = mul2(C, mk(approx_rcp(lo(den)), approx_rcp(hi(den))));   // conjugate root when tca + s cancels
+    const f2 t = mk(lo(ts) < 0.0f ? lo(conj) : lo(sum), hi(ts) < 0.0f ? hi(conj) : hi(sum));
+    px = fma2(vx, t, px); py = fma2(vy, t, py); pz = fma2(vz, t, pz);   // the hit point is the next origin
+    *w = fma2(px, vx, mul2(py, vy));
+    *margin = fma2(px, px, fma2(py, py, bc(-e_rim2)));
+    *guard = fma2(abs2(*w), bc(e_dt_guard), bc(e_rim2_guard));
+    *disc_out = disc;
+}
+
 // Surfaces [from, to) for the two rays of a lane; from/to are warp-uniform.  A ray that is stopped (or was not
 // alive on entry) gets NaN state: every ordered comparison of the decision tests is then false for it, so it
 // marches on next to its live partner without any per-surface bookkeeping.  No lane leaves the loop early (the
@@ -114,26 +149,9 @@ __device__ __forceinline__ void march_pair(const float4* __restrict__ elems, flo
         // the 16 constants of surface i: four 128-bit shared-memory loads, one address for the whole warp
         const float4* ep = elems + 4 * i;
         const float4 q0 = ep[0], q1 = ep[1], q2 = ep[2], q3 = ep[3];
-        const float e_center = q0.x, e_sgn = q0.w, e_rim2 = q1.x, e_eta = q1.y, e_eta2 = q1.z, e_inv_radius = q1.w;
-        const float e_rim2_guard = q2.y, e_dt_guard = q2.z, e_vertex = q2.w;
-        const float e_r2_corr = q3.x, e_miss_guard = q3.y, e_vertex_m2r = q3.z, e_one_m_eta2 = q3.w;
-        const f2 dz = sub2(bc(e_vertex), pz);
-        const f2 m2 = sub2(bc(e_vertex_m2r), pz);                            // dz - 2R
-        const f2 Lz = sub2(bc(e_center), pz);
-        const f2 tca = fma2(Lz, vz, neg2(fma2(px, vx, mul2(py, vy))));
-        // C = |o - c|^2 - radius2 = dz (dz - 2R) + ox^2 + oy^2 + (R^2 - fl(R^2))
-        const f2 C = fma2(dz, m2, fma2(px, px, fma2(py, py, bc(e_r2_corr))));
-        const f2 disc = fma2(tca, tca, neg2(C));
-        const f2 s = mul2(bc(e_sgn), mk(approx_sqrt(fmaxf(lo(disc), 0.0f)), approx_sqrt(fmaxf(hi(disc), 0.0f))));
-        const f2 ts = mul2(tca, s);
-        const f2 den = sub2(tca, s);
-        const f2 sum = add2(tca, s);
-        const f2 conj = mul2(C, mk(approx_rcp(lo(den)), approx_rcp(hi(den))));   // conjugate root when tca + s cancels
-        const f2 t = mk(lo(ts) < 0.0f ? lo(conj) : lo(sum), hi(ts) < 0.0f ? hi(conj) : hi(sum));
-        px = fma2(vx, t, px); py = fma2(vy, t, py); pz = fma2(vz, t, pz);   // the hit point is the next origin
-        const f2 w = fma2(px, vx, mul2(py, vy));
-        const f2 margin = fma2(px, px, fma2(py, py, bc(-e_rim2)));
-        const f2 guard = fma2(abs2(w), bc(e_dt_guard), bc(e_rim2_guard));
+        const float e_center = q0.x, e_eta = q1.y, e_eta2 = q1.z, e_inv_radius = q1.w, e_miss_guard = q3.y, e_one_m_eta2 = q3.w;
+        f2 w, margin, guard, disc;
+        surface_hit(q0, q1, q2, q3, px, py, pz, vx, vy, vz, &w, &margin, &guard, &disc);   // (px, py, pz) becomes the hit point
         const f2 nzr = sub2(bc(e_center), pz);
         const f2 c1 = mul2(fma2(neg2(vz), nzr, w), bc(e_inv_radius));
         const f2 rad = fma2(mul2(bc(e_eta2), c1), c1, bc(e_one_m_eta2));   // 1 - cs2; negative => TIR
@@ -196,8 +214,11 @@ __device__ __forceinline__ void concentric_disk_fast2(f2 u, f2 v, f2* lx, f2* ly
 
 // kSplit >= 0: the stage boundary is a compile-time constant (both stages become straight-line code without
 // per-surface entry/exit tests); kSplit < 0: taken from the camera state at run time.
-template <int kN, int kSplit, bool kImage, bool kLut, bool kInner>
-__global__ void __launch_bounds__(kWarps2 * 32, PoolShape<kInner>::kCtas)
+// kPre: the flavour for cameras whose attempts overwhelmingly die at the FIRST surface (rear rim): stage A is a tight
+// re-sampling loop of (draw, aperture sample, aim, surface-0 intersection + rim test) without refraction; a ray that
+// clears the rim leaves the loop and stage B marches it through the whole stack, surface 0 included.
+template <int kN, int kSplit, bool kImage, bool kLut, bool kInner, bool kPre = false>
+__global__ void __launch_bounds__(kWarps2 * 32, PoolShape<(kInner || kImage || kSplit < 0)>::kCtas)
 kolb_pool2_kernel(const __grid_constant__ CameraState cam, const float4* __restrict__ samples, uint32_t n,
                   uint64_t first_index, uint64_t seed, RayRecord* __restrict__ rays,
                   DeviceStats* stats, unsigned long long* chunk_counter, unsigned long long* queue,
@@ -210,10 +231,10 @@ kolb_pool2_kernel(const __grid_constant__ CameraState cam, const float4* __restr
     float4* elems = reinterpret_cast<float4*>(reinterpret_cast<char*>(s_rows) + rows_bytes);
     for (int i = threadIdx.x; i < 4 * kMaxElements; i += blockDim.x) elems[i] = reinterpret_cast<const float4*>(L.e)[i];
     __syncthreads();
-    constexpr int kSlots2 = PoolShape<kInner>::kSlots;
+    constexpr int kSlots2 = PoolShape<(kInner || kImage || kSplit < 0)>::kSlots;
     WarpPool2<kSlots2>& P = reinterpret_cast<WarpPool2<kSlots2>*>(elems + 4 * kMaxElements)[threadIdx.x >> 5];
     const int count = kN > 0 ? kN : L.count;
-    const int split = kSplit >= 0 ? kSplit : L.split;
+    const int split = kPre ? 0 : (kSplit >= 0 ? kSplit : L.split);   // stage B starts at surface `split`
     const unsigned lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
     LocalStats ls = {0, 0, 0, 0, 0, 0, 0};
@@ -421,10 +442,30 @@ kolb_pool2_kernel(const __grid_constant__ CameraState cam, const float4* __restr
                 y = mul2(y, fma2(mul2(mul2(bc(-0.5f), q), y), y, bc(1.5f)));
                 RayPair a = {fx, fy, bc(L.origin_shift), mul2(dx, y), mul2(dy, y), mul2(bc(dzc), y)};
                 int nrc0, nrc1, v0, v1;
-                march_pair<kN, kInner>(elems, cam.guard_scale, 0, split, a, todo0, todo1, &nrc0, &nrc1, &v0, &v1);
+                if (kPre) {
+                    // surface 0: intersection and rim / miss test only, the arithmetic of the march's first surface.  A ray
+                    // that clears the rim goes on to stage B, which marches the whole stack from the film point (and
+                    // counts the visit to surface 0); a blocked one has visited one surface.
+                    const float4 q0 = elems[0], q1 = elems[1], q2 = elems[2], q3 = elems[3];
+                    f2 hx = a.ox, hy = a.oy, hz = a.oz, w, margin, guard, disc;
+                    surface_hit(q0, q1, q2, q3, hx, hy, hz, a.ux, a.uy, a.uz, &w, &margin, &guard, &disc);
+                    const float miss = q3.y;
+                    const bool s0 = lo(margin) > -lo(guard) || lo(disc) < miss, s1 = hi(margin) > -hi(guard) || hi(disc) < miss;
+                    const bool b0 = lo(disc) < -miss || lo(margin) > lo(guard), b1 = hi(disc) < -miss || hi(margin) > hi(guard);
+                    nrc0 = !s0 ? kPass : (b0 ? kBlocked : kUndecided);
+                    nrc1 = !s1 ? kPass : (b1 ? kBlocked : kUndecided);
+                    v0 = nrc0 == kBlocked ? 1 : 0;
+                    v1 = nrc1 == kBlocked ? 1 : 0;
+                } else {
+                    march_pair<kN, kInner>(elems, cam.guard_scale, 0, split, a, todo0, todo1, &nrc0, &nrc1, &v0, &v1);
+                }
                 if (todo0) { rc0 = nrc0; packed0 += (unsigned)v0 << 16; if (nrc0 == kTir) packed0 += 1u << 9; fresh0 = false; }
                 if (todo1) { rc1 = nrc1; packed1 += (unsigned)v1 << 16; if (nrc1 == kTir) packed1 += 1u << 9; fresh1 = false; }
-                if (kInner) {   // rays that were not re-sampled in this round keep their state
+                if (kPre) {   // the origin stays the film point; only the direction of a re-sampled ray changes
+                    r.ux = mk(todo0 ? lo(a.ux) : lo(r.ux), todo1 ? hi(a.ux) : hi(r.ux));
+                    r.uy = mk(todo0 ? lo(a.uy) : lo(r.uy), todo1 ? hi(a.uy) : hi(r.uy));
+                    r.uz = mk(todo0 ? lo(a.uz) : lo(r.uz), todo1 ? hi(a.uz) : hi(r.uz));
+                } else if (kInner) {   // rays that were not re-sampled in this round keep their state
                     r.ox = mk(todo0 ? lo(a.ox) : lo(r.ox), todo1 ? hi(a.ox) : hi(r.ox));
                     r.oy = mk(todo0 ? lo(a.oy) : lo(r.oy), todo1 ? hi(a.oy) : hi(r.oy));
                     r.oz = mk(todo0 ? lo(a.oz) : lo(r.oz), todo1 ? hi(a.oz) : hi(r.oz));
@@ -437,7 +478,7 @@ kolb_pool2_kernel(const __grid_constant__ CameraState cam, const float4* __restr
                 todo0 = todo0 && (rc0 == kBlocked || rc0 == kTir) && pk2_tries(packed0) <= (unsigned)kMaxTries;
                 todo1 = todo1 && (rc1 == kBlocked || rc1 == kTir) && pk2_tries(packed1) <= (unsigned)kMaxTries;
                 if (!kInner) break;
-                if (__popc(__ballot_sync(0xffffffffu, todo0)) + __popc(__ballot_sync(0xffffffffu, todo1)) < 32) break;
+                if (__popc(__ballot_sync(0xffffffffu, todo0)) + __popc(__ballot_sync(0xffffffffu, todo1)) < (kPre ? kPreKeepGoing : 32)) break;
             }
             bool again[2], onward[2], done[2], und[2];
 #pragma unroll
@@ -492,16 +533,18 @@ static cudaError_t launch_pool2_variant(const CameraState& cam, const float4* sa
             cudaError_t e = cudaMemsetAsync(ws.counters, 0, sizeof(unsigned long long), st);  // chunk cursor only
             if (e != cudaSuccess) return e;
         }
-#define ZP(N, S, INNER)                                                                                                   \
+#define ZPX(N, S, INNER, PRE)                                                                                              \
     do {                                                                                                                 \
-        const unsigned grid = (unsigned)sm_count() * PoolShape<INNER>::kCtas;   /* persistent */                          \
-        const size_t pool_smem = fixed_smem + kWarps2 * sizeof(WarpPool2<PoolShape<INNER>::kSlots>);                     \
-        cudaFuncSetAttribute(kolb_pool2_kernel<N, S, kImage, kLut, INNER>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+        typedef PoolShape<((INNER) || kImage || (S) < 0)> Shape;                                                         \
+        const unsigned grid = (unsigned)sm_count() * Shape::kCtas;   /* persistent */                                    \
+        const size_t pool_smem = fixed_smem + kWarps2 * sizeof(WarpPool2<Shape::kSlots>);                                \
+        cudaFuncSetAttribute(kolb_pool2_kernel<N, S, kImage, kLut, INNER, PRE>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                              (int)pool_smem);                                                                            \
-        kolb_pool2_kernel<N, S, kImage, kLut, INNER><<<grid, threads, pool_smem, st>>>(                                  \
+        kolb_pool2_kernel<N, S, kImage, kLut, INNER, PRE><<<grid, threads, pool_smem, st>>>(                             \
             cam, samples + b, m, first_index + b, seed, rays + b, stats, ws.counters, ws.queue,                          \
             ws.counters + 1, ws.capacity, b);                                                                            \
     } while (0)
+#define ZP(N, S, INNER) ZPX(N, S, INNER, false)
 #define ZPI(N, S) do { if (cam.lens.inner_retry) ZP(N, S, true); else ZP(N, S, false); } while (0)
 // straight-line instantiation when the calibrated stage boundary is the usual one (LUT sampling only)
 #define ZPN(N, S)                                                          \
@@ -512,6 +555,11 @@ static cudaError_t launch_pool2_variant(const CameraState& cam, const float4* sa
         }                                                                  \
         if (!fixed) ZPI(N, -1);                                            \
     } while (0)
+        if (cam.lens.pretest) {   // first-surface-dominated cameras: element count and stage boundary do not matter to stage A
+            ZPX(0, 0, true, true);
+            if (launches) *launches += 1;
+            continue;
+        }
 #ifdef ZOICB_POOL2_TUNE   // tuning builds (tools/build_variants.py): only the two benchmark cameras, quick to compile
         if constexpr (kLut && !kImage) {
             static const int force_inner = [] { const char* v = getenv("ZOICB_INNER"); return v ? atoi(v) : -1; }();
@@ -543,6 +591,7 @@ static cudaError_t launch_pool2_variant(const CameraState& cam, const float4* sa
 #undef ZPN
 #undef ZPI
 #undef ZP
+#undef ZPX
         if (launches) *launches += 1;
     }
     return cudaGetLastError();
