@@ -203,6 +203,19 @@ ZOICB_API zoicb_status zoicb_setup_host_only(const zoicb_params* params, const f
                                    zoicb_constants* out, float* cdfRow, int32_t* rowIndices, float* cdfColumn,
                                    int32_t* columnIndices);
 
+/* Builds the image-based aperture tables of an image on the GPU (the kernels zoicb_create runs for a camera with
+ * useImage; reference imageData::bokehProbability, src/zoic.cpp:222-417) and returns them: cdfRow[h],
+ * rowIndices[h], cdfColumn[w*h], columnIndices[w*h] (each may be NULL).  Entry for entry the tables the reference
+ * builds, tie order of its std::sort calls included.  `ms` (may be NULL) receives the device time of the build. */
+ZOICB_API zoicb_status zoicb_build_bokeh_tables(int device, const float* rgb, int width, int height, int nch,
+                                      float* cdfRow, int32_t* rowIndices, float* cdfColumn, int32_t* columnIndices,
+                                      float* ms);
+
+/* Test hook, host only: orders idx = 0..n-1 by descending values[idx] twice -- with the restatement of libstdc++'s
+ * std::sort the device code uses (csrc/gnu_sort.h) into `restated`, and with the toolchain's own std::sort and the
+ * reference's comparator shape (src/zoic.cpp:317) into `library` -- so a test can show the two agree, ties included. */
+ZOICB_API zoicb_status zoicb_debug_sort_orders(const float* values, int32_t n, int32_t* restated, int32_t* library);
+
 /* Measured fp32 FMA throughput of the device (dependent-chain-free FFMA kernel), in TFLOP/s: the
  * denominator of the fp32 roofline that bench.py reports. */
 ZOICB_API zoicb_status zoicb_measure_fp32_peak(int device, double* tflops);

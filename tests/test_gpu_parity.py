@@ -465,3 +465,63 @@ def test_draw_file_matches_the_reference_draw_build(case, tmp_path):
     cam.close()
     assert got.split("RAYS{")[0] == want.split("RAYS{")[0]          # header
     assert got == want
+
+
+# ---------------------------------------------------------------------------------------------------
+# the image-based aperture tables, built on the GPU (bokeh_build.cu)
+# ---------------------------------------------------------------------------------------------------
+def _bokeh_images():
+    from zoic_b200.synth import hex_bokeh_image
+    rng = np.random.default_rng(17)
+    photo = np.round(rng.random((96, 160, 3)) * 15).astype(np.float32) / 15   # 16 grey levels: ties everywhere
+    photo[rng.random((96, 160)) < 0.3] = 0.0
+    return {
+        "hex255": hex_bokeh_image(255), "hex33-cropped": hex_bokeh_image(33)[:, :20].copy(), "hex32": hex_bokeh_image(32),
+        "flat": np.ones((7, 9, 3), np.float32), "one-row": rng.random((1, 16, 4)).astype(np.float32),
+        "one-column": rng.random((16, 1, 3)).astype(np.float32), "black": np.zeros((5, 5, 3), np.float32),
+        "quantised-photo": photo, "wide": rng.random((3, 5000, 3)).astype(np.float32),
+        "tall": rng.random((700, 40, 3)).astype(np.float32),
+    }
+
+
+def _same_table(a, b):
+    """Bit equality; NaNs (a black image: 0 * inf) only have to be NaNs -- x86 and the GPU sign them differently."""
+    if a.dtype != b.dtype or a.shape != b.shape:
+        return False
+    if a.dtype == np.float32:
+        nan = np.isnan(a)
+        return np.array_equal(nan, np.isnan(b)) and np.array_equal(a[~nan].view(np.uint32), b[~nan].view(np.uint32))
+    return np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("name", ["hex255", "hex33-cropped", "hex32", "flat", "one-row", "one-column", "black",
+                                  "quantised-photo", "wide", "tall"])
+def test_bokeh_tables_built_on_the_gpu_equal_the_oracle_tables(port, name):
+    """cdfRow, rowIndices, cdfColumn, columnIndices entry for entry (float bits, tie order of the sorts included)
+    against the oracle; and a camera created with the image carries the same tables."""
+    from zoic_b200 import ZoicCamera, build_bokeh_tables
+    img = _bokeh_images()[name]
+    kw = dict(lensModel=0, focalLength=3.5, fStop=2.8, useImage=1)
+    p = port.PortCamera(image=img, **kw)
+    want = p.bokeh_tables()
+    p.close()
+    got, ms = build_bokeh_tables(img)
+    assert ms > 0
+    for a, b in zip(got, want):
+        assert _same_table(a, b)
+    cam = ZoicCamera(image=img, **kw)
+    for a, b in zip(cam.bokeh_tables(), want):
+        assert _same_table(a, b)
+    cam.close()
+
+
+def test_bokeh_table_build_large_image_against_the_host_statement():
+    """1024 x 768 photograph-like image (256 grey levels, so thousands of ties per row) against the host statement of
+    the build, which the CPU suite pins to the oracle."""
+    from zoic_b200 import build_bokeh_tables, host_setup
+    rng = np.random.default_rng(23)
+    img = (rng.integers(0, 256, (768, 1024, 3)) / 255.0).astype(np.float32)
+    _, want = host_setup(image=img, lensModel=0, focalLength=3.5, fStop=2.8, useImage=1)
+    got, ms = build_bokeh_tables(img)
+    for a, b in zip(got, want):
+        assert _same_table(a, b)

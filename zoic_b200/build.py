@@ -14,10 +14,10 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.environ.get("ZOICB_LIBDIR") or os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libzoicb.so")
 
-SOURCES = ["capi.cu", "kernels.cu", "kolb_pool.cu", "kolb_pool2.cu", "host_setup.cpp"]
+SOURCES = ["capi.cu", "kernels.cu", "kolb_pool.cu", "kolb_pool2.cu", "bokeh_build.cu", "host_setup.cpp"]
 ADAPTER = "arnold_adapter.cpp"
 PLUGIN = os.path.join(LIBDIR, "libzoic_arnold.so")
-HEADERS = ["camera_state.h", "lens_math.cuh", "host_setup.h", "kernels.h", "kernel_common.cuh",
+HEADERS = ["camera_state.h", "lens_math.cuh", "host_setup.h", "kernels.h", "kernel_common.cuh", "gnu_sort.h",
            os.path.join(ROOT, "include", "zoicb.h"), os.path.join(ROOT, "include", "arnold_shim", "ai.h")]
 
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]

@@ -71,6 +71,27 @@ def host_setup(image=None, **kw):
     return _constants_to_dict(c), (tuple(tabs) if image is not None else None)
 
 
+def build_bokeh_tables(image, device=0):
+    """The image-based aperture tables of `image` ([h, w, nch] floats) built on the GPU:
+    returns ((cdfRow, rowIndices, cdfColumn, columnIndices), device milliseconds)."""
+    lib = capi.load()
+    img = np.ascontiguousarray(image, np.float32)
+    h, w, nch = img.shape
+    tabs = [np.zeros(h, np.float32), np.zeros(h, np.int32), np.zeros(h * w, np.float32), np.zeros(h * w, np.int32)]
+    ms = C.c_float(0.0)
+    capi.check(lib.zoicb_build_bokeh_tables(int(device), img.ctypes.data, w, h, nch, *[t.ctypes.data for t in tabs],
+                                            C.byref(ms)))
+    return tuple(tabs), ms.value
+
+
+def debug_sort_orders(values):
+    """(restated, library): index orders by descending value from csrc/gnu_sort.h and from the toolchain's std::sort."""
+    v = np.ascontiguousarray(values, np.float32)
+    a, b = np.zeros(len(v), np.int32), np.zeros(len(v), np.int32)
+    capi.check(capi.load().zoicb_debug_sort_orders(v.ctypes.data, len(v), a.ctypes.data, b.ctypes.data))
+    return a, b
+
+
 class ZoicCamera:
     """One zoic camera node living on one CUDA device."""
 

@@ -71,6 +71,8 @@ SYMBOLS = {
     "zoicb_get_constants": (C.c_int, [_P, C.POINTER(Constants)]),
     "zoicb_get_bokeh_tables": (C.c_int, [_P, _P, _P, _P, _P]),
     "zoicb_setup_host_only": (C.c_int, [C.POINTER(Params), _P, C.c_int, C.c_int, C.c_int, C.POINTER(Constants), _P, _P, _P, _P]),
+    "zoicb_build_bokeh_tables": (C.c_int, [C.c_int, _P, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, C.POINTER(C.c_float)]),
+    "zoicb_debug_sort_orders": (C.c_int, [_P, C.c_int32, _P, _P]),
     "zoicb_measure_fp32_peak": (C.c_int, [C.c_int, C.POINTER(C.c_double)]),
     "zoicb_kernel_launches": (C.c_uint64, []),
     "zoicb_last_error": (C.c_char_p, []),

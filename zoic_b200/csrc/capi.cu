@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "../../include/zoicb.h"
+#include "gnu_sort.h"
 #include "host_setup.h"
 #include "kernels.h"
 
@@ -66,6 +67,8 @@ struct zoicb_ctx {
     float4* h_in[kSlots] = {nullptr, nullptr, nullptr};   // pinned staging, only for pageable callers
     RayRecord* h_r[kSlots] = {nullptr, nullptr, nullptr};
     std::mutex host_mu;
+    // optional: events recorded around the device-side bokeh table build (zoicb_build_bokeh_tables)
+    cudaEvent_t bokeh_ev0 = nullptr, bokeh_ev1 = nullptr;
 };
 
 namespace {
@@ -95,6 +98,54 @@ bool lut_trace_gpu(void* user, const LensState& lens, const float* film_x, int n
     cudaFree(d_draws);
     cudaFree(d_acc);
     if (!ok) cudaGetLastError();
+    return ok;
+}
+
+// Image-based aperture tables built on the GPU (bokeh_build.cu).  The tables stay on the device in
+// the context; a copy comes back for zoicb_get_bokeh_tables.
+bool bokeh_build_gpu(void* user, const float* rgb, int w, int h, int nch, HostBokeh* out) {
+    zoicb_ctx* c = static_cast<zoicb_ctx*>(user);
+    const size_t np = (size_t)w * h;
+    const size_t ng_row = (size_t)h + kBokehGuidePad, ng_col = (size_t)h * (w + kBokehGuidePad);
+    float *d_rgb = nullptr, *d_work = nullptr, *d_total = nullptr, *d_row_mass = nullptr;
+    int32_t* d_scratch = nullptr;
+    bool ok = false;
+    int launches = 0;
+    do {
+        if (cudaMalloc(&d_rgb, np * nch * sizeof(float)) != cudaSuccess) break;
+        if (cudaMalloc(&d_work, np * sizeof(float)) != cudaSuccess) break;
+        if (cudaMalloc(&d_scratch, np * sizeof(int32_t)) != cudaSuccess) break;
+        if (cudaMalloc(&d_total, 2 * sizeof(float)) != cudaSuccess) break;
+        if (cudaMalloc(&d_row_mass, h * sizeof(float)) != cudaSuccess) break;
+        if (cudaMalloc(&c->d_cdf_row, h * sizeof(float)) != cudaSuccess) break;
+        if (cudaMalloc(&c->d_row_idx, h * sizeof(int32_t)) != cudaSuccess) break;
+        if (cudaMalloc(&c->d_cdf_col, np * sizeof(float)) != cudaSuccess) break;
+        if (cudaMalloc(&c->d_rel_col, np * sizeof(uint16_t)) != cudaSuccess) break;
+        if (cudaMalloc(&c->d_row_guide, ng_row * sizeof(uint16_t)) != cudaSuccess) break;
+        if (cudaMalloc(&c->d_col_guide, ng_col * sizeof(uint16_t)) != cudaSuccess) break;
+        if (cudaMemcpy(d_rgb, rgb, np * nch * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) break;
+        if (c->bokeh_ev0) cudaEventRecord(c->bokeh_ev0, nullptr);
+        if (launch_bokeh_build(d_rgb, w, h, nch, d_work, d_scratch, d_total, d_row_mass, c->d_cdf_row, c->d_row_idx,
+                               c->d_cdf_col, c->d_rel_col, c->d_row_guide, c->d_col_guide, nullptr, &launches) != cudaSuccess) break;
+        if (c->bokeh_ev1) { cudaEventRecord(c->bokeh_ev1, nullptr); cudaEventSynchronize(c->bokeh_ev1); }
+        out->w = w; out->h = h;
+        out->cdf_row.resize(h); out->row_indices.resize(h); out->cdf_column.resize(np); out->column_indices.resize(np);
+        out->row_guide.resize(ng_row); out->col_guide.resize(ng_col);
+        std::vector<uint16_t> rel(np);
+        if (cudaMemcpy(out->cdf_row.data(), c->d_cdf_row, h * sizeof(float), cudaMemcpyDeviceToHost) != cudaSuccess) break;
+        if (cudaMemcpy(out->row_indices.data(), c->d_row_idx, h * sizeof(int32_t), cudaMemcpyDeviceToHost) != cudaSuccess) break;
+        if (cudaMemcpy(out->cdf_column.data(), c->d_cdf_col, np * sizeof(float), cudaMemcpyDeviceToHost) != cudaSuccess) break;
+        if (cudaMemcpy(rel.data(), c->d_rel_col, np * sizeof(uint16_t), cudaMemcpyDeviceToHost) != cudaSuccess) break;
+        if (cudaMemcpy(out->row_guide.data(), c->d_row_guide, ng_row * sizeof(uint16_t), cudaMemcpyDeviceToHost) != cudaSuccess) break;
+        if (cudaMemcpy(out->col_guide.data(), c->d_col_guide, ng_col * sizeof(uint16_t), cudaMemcpyDeviceToHost) != cudaSuccess) break;
+        // the reference's columnIndices hold global pixel indices (row * width + column), src/zoic.cpp:365-391
+        for (int r = 0; r < h; ++r)
+            for (int k = 0; k < w; ++k) out->column_indices[(size_t)r * w + k] = r * w + (int32_t)rel[(size_t)r * w + k];
+        ok = true;
+    } while (0);
+    count_launches(launches);
+    cudaFree(d_rgb); cudaFree(d_work); cudaFree(d_scratch); cudaFree(d_total); cudaFree(d_row_mass);
+    if (!ok) { cudaGetLastError(); out->w = out->h = 0; }
     return ok;
 }
 
@@ -176,35 +227,14 @@ zoicb_status zoicb_create(const zoicb_params* params, const float* rgb, int widt
     zoicb_ctx* c = new zoicb_ctx();
     c->device = device;
     std::string err;
-    zoicb_status rc = build_camera(*params, rgb, width, height, nch, &c->host, &err, lut_trace_gpu, nullptr);
+    zoicb_status rc = build_camera(*params, rgb, width, height, nch, &c->host, &err, lut_trace_gpu, nullptr, bokeh_build_gpu, c);
     if (rc != ZOICB_OK) { free_ctx(c); return fail(rc, "zoicb_create: " + err); }
 
     auto bail = [&](cudaError_t ce, const char* what) { free_ctx(c); return cuda_fail(ce, what); };
     if ((e = cudaMalloc(&c->d_stats, sizeof(DeviceStats))) != cudaSuccess) return bail(e, "cudaMalloc(stats)");
     if ((e = cudaMemset(c->d_stats, 0, sizeof(DeviceStats))) != cudaSuccess) return bail(e, "cudaMemset(stats)");
     const HostBokeh& hb = c->host.bokeh;
-    if (hb.valid()) {
-        const size_t np = (size_t)hb.w * hb.h;
-        std::vector<uint16_t> rel(np);
-        for (int r = 0; r < hb.h; ++r)
-            for (int k = 0; k < hb.w; ++k) {
-                // entry k of ORIGINAL row r (the reference indexes cdfColumn by actual row * width)
-                size_t i = (size_t)r * hb.w + k;
-                rel[i] = (uint16_t)(hb.column_indices[i] - r * hb.w);
-            }
-        if ((e = cudaMalloc(&c->d_cdf_row, hb.h * sizeof(float))) != cudaSuccess) return bail(e, "cudaMalloc");
-        if ((e = cudaMalloc(&c->d_row_idx, hb.h * sizeof(int32_t))) != cudaSuccess) return bail(e, "cudaMalloc");
-        if ((e = cudaMalloc(&c->d_cdf_col, np * sizeof(float))) != cudaSuccess) return bail(e, "cudaMalloc");
-        if ((e = cudaMalloc(&c->d_rel_col, np * sizeof(uint16_t))) != cudaSuccess) return bail(e, "cudaMalloc");
-        cudaMemcpy(c->d_cdf_row, hb.cdf_row.data(), hb.h * sizeof(float), cudaMemcpyHostToDevice);
-        cudaMemcpy(c->d_row_idx, hb.row_indices.data(), hb.h * sizeof(int32_t), cudaMemcpyHostToDevice);
-        cudaMemcpy(c->d_cdf_col, hb.cdf_column.data(), np * sizeof(float), cudaMemcpyHostToDevice);
-        if ((e = cudaMalloc(&c->d_row_guide, hb.row_guide.size() * sizeof(uint16_t))) != cudaSuccess) return bail(e, "cudaMalloc");
-        if ((e = cudaMalloc(&c->d_col_guide, hb.col_guide.size() * sizeof(uint16_t))) != cudaSuccess) return bail(e, "cudaMalloc");
-        cudaMemcpy(c->d_row_guide, hb.row_guide.data(), hb.row_guide.size() * sizeof(uint16_t), cudaMemcpyHostToDevice);
-        cudaMemcpy(c->d_col_guide, hb.col_guide.data(), hb.col_guide.size() * sizeof(uint16_t), cudaMemcpyHostToDevice);
-        if ((e = cudaMemcpy(c->d_rel_col, rel.data(), np * sizeof(uint16_t), cudaMemcpyHostToDevice)) != cudaSuccess)
-            return bail(e, "cudaMemcpy(bokeh tables)");
+    if (hb.valid()) {   // tables were built on the device by bokeh_build_gpu and stayed there
         BokehTables& bt = c->host.state.bokeh;
         bt.cdf_row = c->d_cdf_row; bt.row_indices = c->d_row_idx; bt.cdf_column = c->d_cdf_col; bt.rel_column = c->d_rel_col;
         bt.row_guide = c->d_row_guide; bt.col_guide = c->d_col_guide;
@@ -525,6 +555,47 @@ zoicb_status zoicb_setup_host_only(const zoicb_params* params, const float* rgb,
         if (cdfColumn) std::memcpy(cdfColumn, hb.cdf_column.data(), np * sizeof(float));
         if (columnIndices) std::memcpy(columnIndices, hb.column_indices.data(), np * sizeof(int32_t));
     }
+    return ZOICB_OK;
+}
+
+zoicb_status zoicb_build_bokeh_tables(int device, const float* rgb, int width, int height, int nch, float* cdfRow,
+                                      int32_t* rowIndices, float* cdfColumn, int32_t* columnIndices, float* ms) {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(ZOICB_ERR_CUDA, "zoicb_build_bokeh_tables: no CUDA device (libzoicb has no CPU fallback)");
+    }
+    if (device < 0 || device >= ndev) return fail(ZOICB_ERR_INVALID_ARGUMENT, "zoicb_build_bokeh_tables: bad device index");
+    ZCUDA(cudaSetDevice(device), "cudaSetDevice");
+    std::string err;
+    zoicb_status rc = check_bokeh_image(rgb, width, height, nch, &err);
+    if (rc != ZOICB_OK) return fail(rc, "zoicb_build_bokeh_tables: " + err);
+    zoicb_ctx* c = new zoicb_ctx();
+    c->device = device;
+    HostBokeh hb;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    c->bokeh_ev0 = e0; c->bokeh_ev1 = e1;
+    const bool ok = bokeh_build_gpu(c, rgb, width, height, nch, &hb);
+    if (ok && ms) cudaEventElapsedTime(ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    free_ctx(c);
+    if (!ok) return fail(ZOICB_ERR_CUDA, "zoicb_build_bokeh_tables: device build failed");
+    const size_t np = (size_t)width * height;
+    if (cdfRow) std::memcpy(cdfRow, hb.cdf_row.data(), height * sizeof(float));
+    if (rowIndices) std::memcpy(rowIndices, hb.row_indices.data(), height * sizeof(int32_t));
+    if (cdfColumn) std::memcpy(cdfColumn, hb.cdf_column.data(), np * sizeof(float));
+    if (columnIndices) std::memcpy(columnIndices, hb.column_indices.data(), np * sizeof(int32_t));
+    return ZOICB_OK;
+}
+
+zoicb_status zoicb_debug_sort_orders(const float* values, int32_t n, int32_t* restated, int32_t* library) {
+    if (n < 0 || (n > 0 && !values)) return fail(ZOICB_ERR_INVALID_ARGUMENT, "zoicb_debug_sort_orders: bad argument");
+    if (restated) {
+        for (int32_t i = 0; i < n; ++i) restated[i] = i;
+        gnusort::sort(restated, (long)n, gnusort::Before<int32_t>{values});
+    }
+    if (library) std_sort_desc(values, n, library);
     return ZOICB_OK;
 }
 

@@ -385,13 +385,21 @@ struct ByValueDesc {
     bool operator()(int a, int b) const { return v[a] > v[b]; }
 };
 
-zoicb_status build_bokeh(const float* rgb, int w, int h, int nch, HostBokeh* out, std::string* err) {
+zoicb_status check_bokeh_image_impl(const float* rgb, int w, int h, int nch, std::string* err) {
     if (!rgb || w <= 0 || h <= 0 || nch < 3 || (long long)w * h > (1ll << 26)) {
         *err = "bokeh image needs pixels with at least 3 channels";
         return ZOICB_ERR_BOKEH_IMAGE;
     }
     if (w > 65535) { *err = "bokeh image wider than 65535 pixels"; return ZOICB_ERR_UNSUPPORTED; }
     if (h > kMaxBokehRows) { *err = "bokeh image has more rows than the kernels stage in shared memory (5120)"; return ZOICB_ERR_UNSUPPORTED; }
+    return ZOICB_OK;
+}
+
+// Host statement of the table build: what zoicb_setup_host_only runs (no device), and the yardstick the tables
+// built on the GPU (bokeh_build.cu) are tested against.
+zoicb_status build_bokeh(const float* rgb, int w, int h, int nch, HostBokeh* out, std::string* err) {
+    zoicb_status ok = check_bokeh_image_impl(rgb, w, h, nch, err);
+    if (ok != ZOICB_OK) return ok;
     const int np = w * h;
     std::vector<float> lum(np), pdf(np), row_mass(h), cond(np);
     float total = 0.0f;
@@ -452,9 +460,18 @@ zoicb_status build_bokeh(const float* rgb, int w, int h, int nch, HostBokeh* out
 
 }  // namespace
 
+zoicb_status check_bokeh_image(const float* rgb, int w, int h, int nch, std::string* err) {
+    return check_bokeh_image_impl(rgb, w, h, nch, err);
+}
+
+void std_sort_desc(const float* values, int n, int32_t* idx) {
+    for (int i = 0; i < n; ++i) idx[i] = i;
+    std::sort(idx, idx + n, ByValueDesc{values});
+}
+
 // ------------------------------------------------------------------ node_update (src/zoic.cpp:1575-1720)
 zoicb_status build_camera(const zoicb_params& p, const float* rgb, int w, int h, int nch, HostCamera* out,
-                          std::string* err, LutTraceFn lut_fn, void* lut_user) {
+                          std::string* err, LutTraceFn lut_fn, void* lut_user, BokehBuildFn bokeh_fn, void* bokeh_user) {
     std::memset(&out->state, 0, sizeof out->state);
     std::memset(&out->constants, 0, sizeof out->constants);
     out->params = p;
@@ -472,7 +489,16 @@ zoicb_status build_camera(const zoicb_params& p, const float* rgb, int w, int h,
     else if (p.exposureControl < 0.0f) S.weight_scale = xdiv(1.0f, xadd(1.0f, e2));
 
     if (p.useImage) {
-        zoicb_status rc = build_bokeh(rgb, w, h, nch, &out->bokeh, err);
+        zoicb_status rc;
+        if (bokeh_fn) {
+            rc = check_bokeh_image(rgb, w, h, nch, err);
+            if (rc == ZOICB_OK && !bokeh_fn(bokeh_user, rgb, w, h, nch, &out->bokeh)) {
+                *err = "building the bokeh tables on the device failed";
+                rc = ZOICB_ERR_CUDA;
+            }
+        } else {
+            rc = build_bokeh(rgb, w, h, nch, &out->bokeh, err);
+        }
         if (rc != ZOICB_OK) return rc;
         C.bokehWidth = w; C.bokehHeight = h;
     }

@@ -33,8 +33,19 @@ struct HostCamera {
 typedef bool (*LutTraceFn)(void* user, const LensState& lens, const float* film_x, int n_film,
                            const uint32_t* draws, int samples_per_film, uint8_t* accept);
 
+// A callback that builds the image-based aperture tables (all members of HostBokeh) from a validated image.
+// The C-ABI passes the GPU build (bokeh_build.cu); without one the host statement runs
+// (zoicb_setup_host_only, which has no device).
+typedef bool (*BokehBuildFn)(void* user, const float* rgb, int w, int h, int nch, HostBokeh* out);
+
+// What zoicb_create accepts as a bokeh image (>= 3 channels, <= 65535 columns, <= kMaxBokehRows rows).
+zoicb_status check_bokeh_image(const float* rgb, int w, int h, int nch, std::string* err);
+// idx = 0..n-1 ordered by the toolchain's std::sort with the reference's "greater by value" comparator shape
+void std_sort_desc(const float* values, int n, int32_t* idx);
+
 // Returns ZOICB_OK or an error status; `err` receives a message.
 zoicb_status build_camera(const zoicb_params& p, const float* rgb, int w, int h, int nch, HostCamera* out,
-                          std::string* err, LutTraceFn lut_fn = nullptr, void* lut_user = nullptr);
+                          std::string* err, LutTraceFn lut_fn = nullptr, void* lut_user = nullptr,
+                          BokehBuildFn bokeh_fn = nullptr, void* bokeh_user = nullptr);
 
 }  // namespace zoicb

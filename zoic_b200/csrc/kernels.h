@@ -29,6 +29,12 @@ cudaError_t launch_draw_paths(const CameraState& cam, const float4* samples, uin
                               uint64_t first_index, uint64_t seed,
                               float4* quads, uint8_t* kinds, uint32_t* counts, uint32_t cap, cudaStream_t st, int* launches);
 cudaError_t launch_transform(const float* m3x4, const RayRecord* in, uint64_t n, RayRecord* out, cudaStream_t st, int* launches);
+// Image-based aperture tables built on the device (bokeh_build.cu).  d_work [w*h] floats and d_scratch_idx [w*h]
+// int32 are scratch; d_total [2]; d_row_mass [h]; the remaining pointers are the tables of BokehTables.
+cudaError_t launch_bokeh_build(const float* d_rgb, int w, int h, int nch, float* d_work, int32_t* d_scratch_idx,
+                               float* d_total, float* d_row_mass, float* d_cdf_row, int32_t* d_row_idx,
+                               float* d_cdf_col, uint16_t* d_rel_col, uint16_t* d_row_guide, uint16_t* d_col_guide,
+                               cudaStream_t st, int* launches);
 cudaError_t measure_fp32_peak(double* tflops, int* launches);
 
 }  // namespace zoicb
