@@ -36,6 +36,11 @@ namespace zoicb {
 #ifndef ZOICB_POOL2_ROLLED
 #define ZOICB_POOL2_ROLLED 4
 #endif
+// where the next set-up pass's samples are requested: 0 = at the end of a set-up pass, 1 = at its start (behind the
+// arrival of this pass's samples), 2 = as 0 plus an L2 prefetch two passes ahead
+#ifndef ZOICB_POOL2_PREFETCH
+#define ZOICB_POOL2_PREFETCH 0
+#endif
 constexpr int kRollUnroll = ZOICB_POOL2_ROLLED > 0 ? ZOICB_POOL2_ROLLED : 1;
 constexpr int kWarps2 = ZOICB_POOL2_WARPS;
 // the rim pre-test loop goes round again while at least this many of the 64 rays of the pass still owe an attempt
@@ -326,6 +331,22 @@ kolb_pool2_kernel(const __grid_constant__ CameraState cam, const float4* __restr
             if (take > (int)(end - cur)) take = (int)(end - cur);
             float4 s = pre;
             if (!pre_ok && (int)lane < take) s = __ldcs(samples + cur + lane);
+#if ZOICB_POOL2_PREFETCH == 1
+            // The next set-up pass's samples: the load is issued HERE, right after this pass's samples have arrived (its
+            // address carries a run-time zero made from s.x, so it cannot be scheduled any earlier and never shares a
+            // scoreboard wait with the load above), and the ~270 instructions of this pass cover its latency.  Issued at
+            // the end of the pass instead, the loop-top branch waited for it: 9 % of all warp time (ncu: stall_long_sb
+            // on that one instruction).
+            {
+                // capacity <= 2^27 (get_workspace), so this is zero -- but only at run time
+                const unsigned zero = __float_as_uint(s.x) & (unsigned)(capacity >> 32);
+                pre_ok = take == 32 && cur + 64 <= end;
+                if (pre_ok) pre = __ldcs(samples + cur + 32 + lane + zero);
+            }
+#elif ZOICB_POOL2_PREFETCH == 2
+            // L2 prefetch two passes ahead (no destination register, no scoreboard)
+            if (cur + 96 <= end) asm volatile("prefetch.global.L2 [%0];" ::"l"(samples + cur + 64 + lane));
+#endif
             if ((int)lane < take) {
                 const int slot = P.qf[nF - 1 - lane];
                 const uint32_t idx = cur + lane;
@@ -343,8 +364,10 @@ kolb_pool2_kernel(const __grid_constant__ CameraState cam, const float4* __restr
             __syncwarp();
             // the next set-up pass's samples travel while the march passes in between compute (issued last, so that
             // no scoreboard wait of this pass covers it)
+#if ZOICB_POOL2_PREFETCH != 1
             pre_ok = take == 32 && cur + 32 <= end;
             if (pre_ok) pre = __ldcs(samples + cur + lane);
+#endif
         } else if (mode == 0) {
             // ---------------- stage B: surfaces [split, count) for survivors of stage A
             const bool act0 = (int)lane < m, act1 = (int)lane + 32 < m;
