@@ -1,7 +1,7 @@
 #!/bin/bash
 # times every prebuilt variant under zoic_b200/lib_variants/ (tools/build_variants.py) on the GPU box:
 # headline camera at 32 spp (265 M rays) and the fisheye camera (config4) at 8 spp (265 M rays)
-for d in zoic_b200/lib_variants/*/; do
+for d in zoic_b200/lib_variants/${1:-*}/; do   # optional argument: a glob of variant names
   v=$(basename $d)
   for wl in headline config4; do
     spp=32; [ $wl = config4 ] && spp=8

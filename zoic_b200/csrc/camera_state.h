@@ -80,6 +80,10 @@ struct BokehTables {
     // [guide[floor(u G) - 2], guide[floor(u G) + 3]] and the search only visits a handful of entries
     const uint16_t* row_guide;   // [h + kBokehGuidePad]
     const uint16_t* col_guide;   // [h * (w + kBokehGuidePad)], by actual row like cdf_column
+    // the lens coordinates of a pixel (src/zoic.cpp:441,466,479-484), tabulated with the reference's arithmetic:
+    // dx_of_col[c] = fl(fl(fl(c - (h-1)/2) / fl(w)) * 2), dy_of_row[r] = fl(fl(-fl(r - (w-1)/2) / fl(h)) * 2)
+    const float* dx_of_col;      // [w]
+    const float* dy_of_row;      // [h]
     int32_t w, h;
     int32_t valid;
     int32_t pad;

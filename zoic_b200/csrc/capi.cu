@@ -15,6 +15,7 @@
 #include "gnu_sort.h"
 #include "host_setup.h"
 #include "kernels.h"
+#include "lens_math.cuh"
 
 using namespace zoicb;
 
@@ -53,6 +54,7 @@ struct zoicb_ctx {
     uint16_t* d_rel_col = nullptr;
     uint16_t* d_row_guide = nullptr;
     uint16_t* d_col_guide = nullptr;
+    float* d_dxy = nullptr;   // dx_of_col[w] then dy_of_row[h]
     DeviceStats* d_stats = nullptr;
     // guarded-mode scratch, one per stream the caller uses (stream order serialises reuse)
     std::vector<float> base_guards;
@@ -138,6 +140,13 @@ bool bokeh_build_gpu(void* user, const float* rgb, int w, int h, int nch, HostBo
         if (cudaMemcpy(rel.data(), c->d_rel_col, np * sizeof(uint16_t), cudaMemcpyDeviceToHost) != cudaSuccess) break;
         if (cudaMemcpy(out->row_guide.data(), c->d_row_guide, ng_row * sizeof(uint16_t), cudaMemcpyDeviceToHost) != cudaSuccess) break;
         if (cudaMemcpy(out->col_guide.data(), c->d_col_guide, ng_col * sizeof(uint16_t), cudaMemcpyDeviceToHost) != cudaSuccess) break;
+        {   // lens coordinates per column / per row, with the reference's operations (src/zoic.cpp:441,466,479-484)
+            std::vector<float> dxy((size_t)w + h);
+            for (int col = 0; col < w; ++col) dxy[col] = xmul(xdiv((float)(col - (h - 1) / 2), (float)w), 2.0f);
+            for (int row = 0; row < h; ++row) dxy[(size_t)w + row] = xmul(xdiv(xmul((float)(row - (w - 1) / 2), -1.0f), (float)h), 2.0f);
+            if (cudaMalloc(&c->d_dxy, dxy.size() * sizeof(float)) != cudaSuccess) break;
+            if (cudaMemcpy(c->d_dxy, dxy.data(), dxy.size() * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) break;
+        }
         // the reference's columnIndices hold global pixel indices (row * width + column), src/zoic.cpp:365-391
         for (int r = 0; r < h; ++r)
             for (int k = 0; k < w; ++k) out->column_indices[(size_t)r * w + k] = r * w + (int32_t)rel[(size_t)r * w + k];
@@ -179,7 +188,7 @@ void free_ctx(zoicb_ctx* c) {
     cudaSetDevice(c->device);
     for (auto& kv : c->workspaces) { cudaFree(kv.second.counters); cudaFree(kv.second.queue); }
     cudaFree(c->d_cdf_row); cudaFree(c->d_row_idx); cudaFree(c->d_cdf_col); cudaFree(c->d_rel_col);
-    cudaFree(c->d_row_guide); cudaFree(c->d_col_guide);
+    cudaFree(c->d_row_guide); cudaFree(c->d_col_guide); cudaFree(c->d_dxy);
     cudaFree(c->d_stats);
     for (int s = 0; s < zoicb_ctx::kSlots; ++s) {
         if (c->streams[s]) cudaStreamDestroy(c->streams[s]);
@@ -238,6 +247,7 @@ zoicb_status zoicb_create(const zoicb_params* params, const float* rgb, int widt
         BokehTables& bt = c->host.state.bokeh;
         bt.cdf_row = c->d_cdf_row; bt.row_indices = c->d_row_idx; bt.cdf_column = c->d_cdf_col; bt.rel_column = c->d_rel_col;
         bt.row_guide = c->d_row_guide; bt.col_guide = c->d_col_guide;
+        bt.dx_of_col = c->d_dxy; bt.dy_of_row = c->d_dxy + hb.w;
         bt.w = hb.w; bt.h = hb.h; bt.valid = 1;
     }
     *out = c;

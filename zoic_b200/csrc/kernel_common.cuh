@@ -7,6 +7,10 @@
 #include "kernels.h"
 #include "lens_math.cuh"
 
+#ifndef ZOICB_BOKEH_DXY_TABLES
+#define ZOICB_BOKEH_DXY_TABLES 1   // +2..3 % on config 3 (profiles/r01b_ab.txt); 0 = the divisions in the kernel
+#endif
+
 namespace zoicb {
 
 constexpr int kChunk = 2048;   // samples handed to a warp per grab of the global cursor (multiple of 32)
@@ -64,6 +68,8 @@ struct BokehView {
     const uint16_t* rel_col;
     const uint16_t* row_guide;
     const uint16_t* col_guide;
+    const float* dx_of_col;
+    const float* dy_of_row;
     int w, h;
 };
 
@@ -78,11 +84,18 @@ __device__ __forceinline__ void bokeh_sample(const BokehView& b, float u_row, fl
     int c = upper_bound_guided(b.w, u_col, [&](int i) { return __ldg(col + i); }, [&](int k) { return (int)__ldg(cg + k); });
     if (c >= b.w) c = b.w - 1;
     const int rel = (int)__ldg(b.rel_col + start + c);
+#if ZOICB_BOKEH_DXY_TABLES
+    // the two divisions below depend on the column / the row only: tabulated once per camera with the same operations
+    (void)rrow;
+    *dx = __ldg(b.dx_of_col + rel);
+    *dy = __ldg(b.dy_of_row + row);
+#else
     const int rcol = rel - ((b.h - 1) / 2);  // centred with the HEIGHT (:466)
     const float fr = (float)rcol;
     const float fc = xmul((float)rrow, -1.0f);
     *dx = xmul(xdiv(fr, (float)b.w), 2.0f);
     *dy = xmul(xdiv(fc, (float)b.h), 2.0f);
+#endif
 }
 
 template <bool kImage>
@@ -107,6 +120,8 @@ __device__ __forceinline__ BokehView stage_bokeh(const CameraState& cam) {
     b.rel_col = cam.bokeh.rel_column;
     b.row_guide = cam.bokeh.row_guide;
     b.col_guide = cam.bokeh.col_guide;
+    b.dx_of_col = cam.bokeh.dx_of_col;
+    b.dy_of_row = cam.bokeh.dy_of_row;
     for (int i = threadIdx.x; i < b.h; i += blockDim.x) {
         s_rows[i] = cam.bokeh.cdf_row[i];
         s_rows[b.h + i] = __int_as_float(cam.bokeh.row_indices[i]);

@@ -131,8 +131,12 @@ kolb_exact_persistent_kernel(const __grid_constant__ CameraState cam, const floa
 // arithmetic (the thin-lens attempt has no double-precision step, so exactness costs little): results are
 // bit-identical to thin_exact_sample, only the order of work differs.
 // ------------------------------------------------------------------------------------------------
+#ifndef ZOICB_THIN_CTAS
+#define ZOICB_THIN_CTAS 6   // resident CTAs of 8 warps per SM: 48 warps at <= 40 registers (4 -> 5 -> 6: 14.7 -> 16.3 -> 17.2 Grays/s on
+                           // config 3, profiles/r01b_ab.txt; 8 spills)
+#endif
 template <bool kImage>
-__global__ void __launch_bounds__(256, 4)
+__global__ void __launch_bounds__(256, ZOICB_THIN_CTAS)
 thin_persistent_kernel(const __grid_constant__ CameraState cam, const float4* __restrict__ samples, uint64_t n,
                        uint64_t first_index, uint64_t seed, RayRecord* __restrict__ rays,
                        DeviceStats* stats, int stage_rows, unsigned long long* chunk_counter) {
@@ -412,13 +416,29 @@ static cudaError_t launch_variant(const CameraState& cam, int mode, const float4
     if (mode == 1 && kModel == 0 && cam.thin.use_dof && cam.thin.use_ov) {  // retry loop present: persistent schedule
         cudaError_t e = cudaMemsetAsync(ws.counters, 0, 4 * sizeof(unsigned long long), st);
         if (e != cudaSuccess) return e;
-        thin_persistent_kernel<kImage><<<(unsigned)sm_count() * 4, threads, smem, st>>>(cam, samples, n, first_index, seed, rays,
+        thin_persistent_kernel<kImage><<<(unsigned)sm_count() * ZOICB_THIN_CTAS, threads, smem, st>>>(cam, samples, n, first_index, seed, rays,
                                                                                       stats, stage, ws.counters);
         if (launches) *launches += 1;
         return cudaGetLastError();
     }
-    exact_kernel<kModel, kImage, kLut><<<grid_for(n, threads, 8), threads, smem, st>>>(cam, samples, n, first_index, seed,
-                                                                                     rays, stats, stage);
+    // grid = the CTAs that are resident at once (register-limited: 6 of 256 threads for the thin lens), so the grid-stride
+    // loop runs as ONE wave; with a fixed 8 per SM the last 2 of every 8 CTAs ran as a second, mostly empty wave
+    static const int resident = [] {
+        int b = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, exact_kernel<kModel, kImage, kLut>, 256, 0) != cudaSuccess || b <= 0) {
+            cudaGetLastError();
+            b = 4;
+        }
+        return b;
+    }();
+    int ctas = resident;
+    if (smem > 0) {   // row tables in dynamic shared memory can lower the residency: ask again for this size
+        int b = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, exact_kernel<kModel, kImage, kLut>, threads, smem) == cudaSuccess && b > 0) ctas = b;
+        else cudaGetLastError();
+    }
+    exact_kernel<kModel, kImage, kLut><<<grid_for(n, threads, ctas), threads, smem, st>>>(cam, samples, n, first_index, seed,
+                                                                                        rays, stats, stage);
     if (launches) *launches += 1;
     return cudaGetLastError();
 }
