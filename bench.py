@@ -8,7 +8,7 @@
 A "step" is one pass of the hot path (zoicb_generate, i.e. camera_create_ray for a whole batch) over one
 batch of synthetic samples that is already resident in HBM.  The default workload is the headline metric of
 BASELINE.json: the Kolb double-Gauss f/2.0 camera on a 3840x2160x256spp sample grid (2.12 G rays per GPU per
-step; every rank takes its own contiguous 2.12 G-sample shard of a 256*N spp job: weak scaling, no data-path
+step; rank r takes pass r -- its own 256 samples of every pixel -- of a 256*N spp job: weak scaling, no data-path
 collective).  Rank 0 prints ONE JSON line; see DESIGN.md section 7 for every key.
 """
 import argparse
@@ -208,12 +208,17 @@ def main():
     free, _total = torch.cuda.mem_get_info(dev)
     while n * 48 > free * 0.9:
         n //= 2
-    first = rank * n  # rank r owns samples [r*n, (r+1)*n) of the (spp * world) job: weak scaling
+    # Weak scaling: rank r owns samples [r*n, (r+1)*n) of a W x H x spp x world job laid out PASS-major -- sample index
+    # i = pass * (W*H*spp) + pixel * spp + s -- so every rank renders the whole film once (its own spp samples of every
+    # pixel, its own retry streams) and all ranks carry the same mix of vignetted and clear pixels.  (Pixel-major bands
+    # gave the ranks with the film's top and bottom rows 2.48 instead of 2.07 attempts per ray: 89 % efficiency at 8 GPUs
+    # from load imbalance alone, profiles/r01c_bench_headline_8gpu_bands.json.)
+    first = rank * n
     samples = torch.empty((n, 4), dtype=torch.float32, device=dev)
     tile = 1 << 28
     for b in range(0, n, tile):
         m = min(tile, n - b)
-        cam.synth_samples(wl.W, wl.H, wl.spp * world, wl.seed, first + b, m, out=samples[b:b + m])
+        cam.synth_samples(wl.W, wl.H, wl.spp, wl.seed, first + b, m, out=samples[b:b + m])   # pixel index wraps per pass
     rays = torch.empty((n, 8), dtype=torch.float32, device=dev)   # one 32-byte zoicb_ray per sample
     torch.cuda.synchronize()
 
@@ -339,7 +344,8 @@ def main():
         cfg.update({"samples_per_gpu_per_step": n, "arithmetic_mode": mode_name,
                     "l2": ("inputs (%.1f GB per step) are larger than L2; no flush needed" % (16.0 * n / 1e9)) if 16.0 * n > 2.6e8
                           else "batch (%.0f MB in + out) fits in L2: the number is L2-assisted" % (48.0 * n / 1e6),
-                    "sharding": "rank r owns samples [r*n,(r+1)*n) of the %dx%dx%d grid" % (wl.W, wl.H, wl.spp * world)})
+                    "sharding": "rank r owns samples [r*n,(r+1)*n) of a %dx%dx%d-spp job in %d pass-major passes of %d spp: "
+                                "every rank renders the whole film, no data-path collective" % (wl.W, wl.H, wl.spp * world, world, wl.spp)})
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg, "clocks": clocks,

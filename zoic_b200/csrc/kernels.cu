@@ -414,6 +414,9 @@ static cudaError_t launch_variant(const CameraState& cam, int mode, const float4
         return cudaGetLastError();
     }
     if (mode == 1 && kModel == 0 && cam.thin.use_dof && cam.thin.use_ov) {  // retry loop present: persistent schedule
+        // (a slot-pool version of this kernel -- set-up pass / attempt pass over a shared-memory pool, like the raytraced
+        // kernels -- was tried and dropped: the two table searches, not the divergent regeneration, are what an attempt
+        // costs, and the pool's shared-memory traffic made it slower, 12.4-15.0 against 17.6 Grays/s; profiles/r01b_ab.txt)
         cudaError_t e = cudaMemsetAsync(ws.counters, 0, 4 * sizeof(unsigned long long), st);
         if (e != cudaSuccess) return e;
         thin_persistent_kernel<kImage><<<(unsigned)sm_count() * ZOICB_THIN_CTAS, threads, smem, st>>>(cam, samples, n, first_index, seed, rays,
