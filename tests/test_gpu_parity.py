@@ -525,3 +525,70 @@ def test_bokeh_table_build_large_image_against_the_host_statement():
     got, ms = build_bokeh_tables(img)
     for a, b in zip(got, want):
         assert _same_table(a, b)
+
+
+# ---------------------------------------------------------------------------------------------------
+# BASELINE.json's full sizes: size-independent properties + oracle windows inside the big batch
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["headline", "config3", "config4"])
+def test_full_size_batches_hold_the_invariants(port, name):
+    """One zoicb_generate over the whole configuration (2.12 G samples; config 4 is halved until it fits the device).
+    Checked: every record written once, counters add up, weights are 0 or the exposure scale, live directions are unit
+    vectors, tries <= 26; three 2^16-sample windows (start, middle, end) equal their own small launches bit for bit
+    (batch boundaries do not matter) and match the oracle (bit-exact for the thin lens, zero path flips and the 1e-5
+    tolerance for the guarded raytraced lens)."""
+    from zoic_b200 import ZoicCamera
+    from zoic_b200 import workloads
+    wl = workloads.BY_NAME[name]()
+    n = wl.n
+    free, _ = torch.cuda.mem_get_info()
+    while n * 48 > free * 0.85:
+        n //= 2
+    if n < (1 << 28):
+        pytest.skip("not enough device memory for a full-size batch")
+    image = wl.image()
+    cam = ZoicCamera(image=image, **wl.params)
+    s = torch.empty((n, 4), dtype=torch.float32, device="cuda")
+    tile = 1 << 27
+    for b in range(0, n, tile):
+        m = min(tile, n - b)
+        cam.synth_samples(wl.W, wl.H, wl.spp, wl.seed, b, m, out=s[b:b + m])
+    rays = torch.full((n, 8), float("nan"), device="cuda")
+    cam.reset_stats()
+    cam.create_rays(s, seed=wl.seed, first_index=0, out=rays)
+    torch.cuda.synchronize()
+    st = cam.stats()
+    live = tries_sum = 0
+    worst = 0.0
+    for b in range(0, n, tile):
+        r = rays[b:b + tile]
+        w, t = r[:, 3], r[:, 7]
+        assert not torch.isnan(w).any() and not torch.isnan(t).any()
+        assert bool(((w == 0) | (w == 1)).all()) and float(t.max()) <= 26 and float(t.min()) >= 0
+        alive = w != 0
+        live += int(alive.sum())
+        tries_sum += int(t.sum(dtype=torch.float64))
+        d = r[:, 4:7]
+        err = ((d * d).sum(1) - 1).abs()
+        worst = max(worst, float(err[alive].max()) if bool(alive.any()) else 0.0)
+        assert bool(torch.isfinite(r[:, :7][alive]).all())
+    assert st["rays"] == n and st["success"] + st["vignetted"] == n
+    assert st["success"] == live and st["attempts"] == n + tries_sum
+    assert worst <= 1e-5, worst   # |d|^2 - 1 of live rays
+    ref = port.PortCamera(image=image, **wl.params)
+    k = 1 << 16
+    for a in (0, (n // 2) - 12345, n - k):
+        win = s[a:a + k].contiguous()
+        again = cam.create_rays(win, seed=wl.seed, first_index=a)
+        torch.cuda.synchronize()
+        assert torch.equal(again.view(torch.int32), rays[a:a + k].view(torch.int32))
+        g = again.cpu().numpy()
+        o_ref, d_ref, _ = ref.generate(win.cpu().numpy(), seed=wl.seed, first_index=a, nthreads=8)
+        res = compare_rays(g[:, :4], g[:, 4:], o_ref, d_ref)
+        assert res["path_flips"] == 0 and res["out_of_tol"] == 0, res
+        if wl.params["lensModel"] == 0:
+            assert bits_equal(g[:, :4], o_ref) and bits_equal(g[:, 4:], d_ref)
+    cam.close()
+    ref.close()
+    del s, rays
+    torch.cuda.empty_cache()
