@@ -100,14 +100,17 @@ bokeh_pdf_rowmass_kernel(float* __restrict__ pdf, const float* __restrict__ tota
     if (r0 + lane < h) row_mass[r0 + lane] = acc;
 }
 
-// cutpoints of one CDF (camera_state.h): g[k] = first index whose value is greater than fl(k / n), k <= n; n beyond
+// cutpoints of one CDF (camera_state.h): g[k] = first index whose value is greater than fl(k / n), k <= n, clamped to
+// the start of the flat tail; the tail start beyond
 __device__ void build_guide(const float* cdf, int n, uint16_t* g) {
+    int tail = n;   // start of the flat tail: the first entry that already carries the final value (n for a NaN table)
+    for (int i = 0; i < n; ++i) if (cdf[i] >= cdf[n - 1]) { tail = i; break; }
     int pos = 0;
     for (int k = 0; k < n + kBokehGuidePad; ++k) {
-        if (k > n) { g[k] = (uint16_t)n; continue; }
+        if (k > n) { g[k] = (uint16_t)tail; continue; }
         const float t = xdiv((float)k, (float)n);
         while (pos < n && !(t < cdf[pos])) ++pos;
-        g[k] = (uint16_t)pos;
+        g[k] = (uint16_t)(pos < tail ? pos : tail);
     }
 }
 

@@ -75,9 +75,10 @@ struct BokehTables {
     const int32_t* row_indices;  // [h]
     const float* cdf_column;     // [h*w], rows in ORIGINAL row order (indexed by actual row * w)
     const uint16_t* rel_column;  // [h*w], columnIndices[c] - row*w
-    // guide ("cutpoint") tables of the two inverse-CDF searches: guide[k] = upper_bound(cdf, fl(k / G)) for
-    // k <= G, = n beyond (G = n = table length; kBokehGuidePad extra entries), so that the answer for u lies in
-    // [guide[floor(u G) - 2], guide[floor(u G) + 3]] and the search only visits a handful of entries
+    // guide ("cutpoint") tables of the two inverse-CDF searches: guide[k] = min(upper_bound(cdf, fl(k / G)), T) for
+    // k <= G, = T beyond (G = n = table length; kBokehGuidePad extra entries; T = start of the CDF's flat tail, the
+    // first entry that carries the final value), so that the answer for u < final lies in
+    // [guide[floor(u G) - 2], guide[floor(u G) + 3]] and the search only visits a handful of entries; u >= final => n
     const uint16_t* row_guide;   // [h + kBokehGuidePad]
     const uint16_t* col_guide;   // [h * (w + kBokehGuidePad)], by actual row like cdf_column
     // the lens coordinates of a pixel (src/zoic.cpp:441,466,479-484), tabulated with the reference's arithmetic:

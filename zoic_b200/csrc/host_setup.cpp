@@ -443,12 +443,15 @@ zoicb_status build_bokeh(const float* rgb, int w, int h, int nch, HostBokeh* out
     // guide tables for the device-side searches (camera_state.h): they only narrow the range the search visits,
     // the result stays std::upper_bound's
     auto guide = [](const float* cdf, int n, uint16_t* g) {
+        // start of the flat tail: the first entry that already carries the final value (n when the table is NaN)
+        int tail = n;
+        for (int i = 0; i < n; ++i) if (cdf[i] >= cdf[n - 1]) { tail = i; break; }
         int pos = 0;
         for (int k = 0; k < n + kBokehGuidePad; ++k) {
-            if (k > n) { g[k] = (uint16_t)n; continue; }
+            if (k > n) { g[k] = (uint16_t)tail; continue; }
             const float t = (float)k / (float)n;
             while (pos < n && !(t < cdf[pos])) ++pos;   // first index whose value is greater than t; t grows with k
-            g[k] = (uint16_t)pos;
+            g[k] = (uint16_t)(pos < tail ? pos : tail);
         }
     };
     out->row_guide.resize(h + kBokehGuidePad);

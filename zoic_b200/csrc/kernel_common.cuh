@@ -7,6 +7,9 @@
 #include "kernels.h"
 #include "lens_math.cuh"
 
+#ifndef ZOICB_BOKEH_COUNT
+#define ZOICB_BOKEH_COUNT 0   // 8: resolve brackets of up to 8 entries by counting (independent loads); 0: always halve
+#endif
 #ifndef ZOICB_BOKEH_DXY_TABLES
 #define ZOICB_BOKEH_DXY_TABLES 1   // +2..3 % on config 3 (profiles/r01b_ab.txt); 0 = the divisions in the kernel
 #endif
@@ -30,20 +33,37 @@ __device__ __forceinline__ void store_ray(RayRecord* __restrict__ rays, uint64_t
 // brackets the answer: with k = floor(u n) -- computed in fp32, so off by at most one -- the thresholds
 // fl((k-2)/n) <= u < fl((k+3)/n) hold with room for every rounding involved, hence
 //   guide[k-2] <= answer <= guide[k+3],
-// and the libstdc++ first/len halving runs over that handful of entries only (a uniform u meets about five of
-// them on average, whatever the image).  u >= 1 lands on the padded tail (= n); NaN and negative u take the whole
-// range.  The loop runs a warp-uniform number of rounds with predicated updates: no divergence, and -- the reason
-// it is written this way -- no lane leaves the loop early.  (With a data-dependent trip count ptxas 12.9 let the
+// a handful of entries (a uniform u meets about four of them on average, whatever the image).  The guide entries are
+// clamped to the start of the CDF's flat tail (the zero-probability pixels around the aperture shape all carry the final
+// value): u >= final is answered directly (= n), anything smaller lies at or before the tail, so no bracket ever spans
+// it (without the clamp a quarter of all warps had one lane whose bracket was the whole tail).
+// Brackets of up to 8 entries -- all of them for the benchmark image -- are resolved by COUNTING the entries that are
+// not greater than u: eight independent loads instead of three dependent ones.  Longer brackets (warp-uniform
+// decision), NaN and negative u (whole range) take the libstdc++ first/len halving with a warp-uniform number of
+// rounds and predicated updates: no lane leaves the loop early.  (With a data-dependent trip count ptxas 12.9 let the
 // early lanes run ahead and re-use the uniform registers that hold the table pointers while the late lanes were
 // still reading them.)
 template <typename Load, typename Guide>
 __device__ __forceinline__ int upper_bound_guided(int n, float u, Load load, Guide guide) {
     int first = 0, len = n;
+    bool past = false;
     if (u >= 0.0f) {
         const float f = u * (float)n;
         const int k = f >= (float)n ? n : (int)f;
         first = guide(k >= 2 ? k - 2 : 0);
         len = guide(k + 3) - first;
+        past = u >= load(n - 1);   // false for a NaN table (black image): those guides are not clamped
+    }
+    constexpr int kCount = ZOICB_BOKEH_COUNT;
+    if (kCount > 0 && __all_sync(__activemask(), len <= kCount)) {
+        int cnt = 0;
+#pragma unroll
+        for (int j = 0; j < kCount; ++j) {
+            const int i = first + j;
+            const float v = load(i < n ? i : n - 1);
+            cnt += (j < len && !(u < v)) ? 1 : 0;
+        }
+        return past ? n : first + cnt;
     }
     const int rounds = 32 - __clz(__reduce_max_sync(__activemask(), (unsigned)len));
     for (int it = 0; it < rounds; ++it) {
@@ -55,7 +75,7 @@ __device__ __forceinline__ int upper_bound_guided(int n, float u, Load load, Gui
         first = (live && !left) ? mid + 1 : first;
         len = live ? (left ? half : len - half - 1) : 0;
     }
-    return first;
+    return past ? n : first;
 }
 
 // The row tables (cdfRow, rowIndices: 8 bytes per image row) are always staged in dynamic shared memory --
