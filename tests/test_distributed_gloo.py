@@ -70,3 +70,24 @@ def test_two_rank_sharding_and_gather_match_single_process(tmp_path):
     o, d, st = cam.generate(s, seed=wl.seed, first_index=base)
     assert bits_equal(got["o"], o) and bits_equal(got["d"], d)
     assert list(got["stats"]) == [st[k] for k in sorted(st)]
+
+
+def test_pass_major_shards_render_the_whole_film():
+    """bench.py's layout: rank r owns samples [r*n, (r+1)*n) of a W x H x spp job repeated
+    `world` times, n = W*H*spp.  The pixel of sample i wraps per pass, so every rank covers every pixel with its
+    own spp samples -- the same work mix on every rank -- and no two ranks share a sample."""
+    from oracle import port
+    port.load()
+    W, H, spp, world, seed = 12, 8, 4, 3, 77
+    n = W * H * spp
+    shards = [port.synth_samples(W, H, spp, seed, r * n, n) for r in range(world)]
+    for s in shards:
+        px = np.floor((s[:, 0] + 1.0) * 0.5 * W).astype(int)
+        py = np.floor((1.0 - s[:, 1] * (W / H)) * 0.5 * H).astype(int)
+        counts = np.zeros((H, W), int)
+        np.add.at(counts, (np.clip(py, 0, H - 1), np.clip(px, 0, W - 1)), 1)
+        assert (counts == spp).all()          # every pixel, spp samples each
+    for a in range(world):
+        for b in range(a + 1, world):
+            assert not np.array_equal(shards[a], shards[b])
+            assert len(set(map(bytes, shards[a])) & set(map(bytes, shards[b]))) == 0
