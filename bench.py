@@ -338,6 +338,8 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu:
         cpu = cpu_reference_rate(wl, args.cpu_samples)
         cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        one = cpu_reference_rate(wl, max(args.cpu_samples // 16, 8192), cores=1)   # the 1-thread figure too
+        cpu["one_core"] = {"value": one["value"], "unit": UNIT, "sample": one["sample"]}
 
     if rank == 0:
         cfg = wl.describe()
