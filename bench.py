@@ -193,6 +193,9 @@ def main():
         raise SystemExit("bench.py: no CUDA device; the product has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     if world > 1:
+        # stdout carries the one JSON line and nothing else: NCCL's version / debug lines (NCCL_DEBUG set by the box) go
+        # to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
 
