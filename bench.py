@@ -25,6 +25,27 @@ if ROOT not in sys.path:
 METRIC = "camera Mrays/s"
 UNIT = "Mrays/s"
 
+_JSON_FD = None
+
+
+def claim_stdout():
+    """stdout carries the ONE JSON line and nothing else: keep the real stdout aside and point file descriptor 1 at stderr,
+    so that whatever libraries print there (NCCL's version line, torchrun banners of child processes) cannot mix in."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
 
 def flops_per_batch(model, stats):
     """Algorithmic fp32 flops (DESIGN.md section 6 / SURVEY.md 8(d)) from the kernel's exact counters."""
@@ -150,7 +171,7 @@ def run_reference_arm(args, wl):
                              "sample": last["sample"]},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -172,6 +193,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
+    claim_stdout()
 
     from zoic_b200 import workloads
     wl = workloads.BY_NAME[args.workload]()
@@ -193,9 +215,6 @@ def main():
         raise SystemExit("bench.py: no CUDA device; the product has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     if world > 1:
-        # stdout carries the one JSON line and nothing else: NCCL's version / debug lines (NCCL_DEBUG set by the box) go
-        # to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
 
@@ -358,7 +377,7 @@ def main():
                 "stats": stats}
         if gather:
             line["gather"] = gather
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
