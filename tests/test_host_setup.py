@@ -160,3 +160,22 @@ def test_error_codes(tmp_path):
     with pytest.raises(capi.ZoicError) as e:
         host_setup(lensModel=7)
     assert e.value.code == capi.ERR_INVALID_ARGUMENT
+
+
+def test_kolb_setup_random_parameters_all_lenses(port):
+    """Seeded sweep over the node parameters' documented ranges (src/zoic.mtd) for every lens table: the derived
+    constants, the rescaled element stack and all 32 exit-pupil boxes equal the oracle's bit for bit."""
+    rng = np.random.default_rng(20261017)
+    for lens in sorted(LENSES):
+        fnum, focal = LENSES[lens]
+        for _ in range(2):
+            kw = dict(lensModel=1, lensDataPath=lens_path(lens),
+                      focalLength=float(np.float32(focal * rng.uniform(0.6, 1.8))),
+                      fStop=float(np.float32(rng.choice([1.0, 1.4, 2.0, 2.8, 4.0, 5.6, 8.0, 16.0]))),
+                      focalDistance=float(np.float32(rng.uniform(15.0, 2000.0))),
+                      sensorWidth=float(np.float32(rng.uniform(1.0, 4.5))),
+                      kolbSamplingLUT=int(rng.integers(0, 2)))
+            c, _ = host_setup(**kw)
+            p = port.PortCamera(**kw)
+            _same_constants(c, p.constants())
+            p.close()

@@ -82,3 +82,68 @@ def test_reference_draw_build_reproduces_its_own_fixture(tmp_path):
     got = open(tmp_path / "draw.zoic").read().split("\n")[:10]
     want = [l.rstrip("\n") for l in open(os.path.join(GOLDEN, "draw_zoic_header.txt"))]
     assert got == want
+
+
+def _tied_image(h=48, w=64, levels=8, seed=3):
+    """A photograph-like aperture image with few grey levels: hundreds of exactly equal pixels per row and equal row
+    masses, so that the order std::sort leaves ties in (src/zoic.cpp:317, :381) decides which pixel a sample lands on."""
+    rng = np.random.default_rng(seed)
+    img = np.round(rng.random((h, w, 3)) * (levels - 1)).astype(np.float32) / (levels - 1)
+    img[:, :, 1] = img[:, :, 0]
+    img[:, :, 2] = img[:, :, 0]
+    img[rng.random((h, w)) < 0.25] = 0.0
+    img[5] = img[9]          # two rows with identical masses
+    return img
+
+
+@pytest.mark.parametrize("kw", [dict(lensModel=0, focalLength=3.5, fStop=2.8, opticalVignettingDistance=2.0, useImage=1),
+                                dict(lens="double_gauss_f2.0.dat", useImage=1)], ids=["thin-ov", "dg"])
+def test_tie_order_of_the_table_sorts_equals_the_compiled_reference(port, kw):
+    ref = _ref()
+    from zoic_b200.workloads import LENSES, lens_path
+    kw = dict(kw)
+    if "lens" in kw:
+        lens = kw.pop("lens")
+        fnum, focal = LENSES[lens]
+        kw = dict(dict(lensModel=1, lensDataPath=lens_path(lens), focalLength=focal, fStop=fnum), **kw)
+    image = _tied_image()
+    r = ref.RefCamera(image=image, **kw)
+    p = port.PortCamera(image=image, **kw)
+    s = random_samples(30_000, seed=9)
+    o, d, st = r.generate(s, seed=5, first_index=0)
+    o2, d2, st2 = p.generate(s, seed=5, first_index=0, nthreads=4)
+    assert bits_equal(o, o2) and bits_equal(d, d2)
+    assert st["attempts"] == st2["attempts"]
+    # the samples really do land on tied pixels: the image has 8 grey levels over 3072 pixels
+    lum = image @ np.array([0.3, 0.59, 0.11], np.float32)
+    assert len(np.unique(lum)) <= 8
+    r.close()
+    p.close()
+
+
+def test_port_equals_compiled_reference_on_random_parameters(port):
+    """Seeded sweep of node parameters over every lens table and the thin lens (2 000 samples each)."""
+    ref = _ref()
+    from zoic_b200.workloads import LENSES, lens_path
+    rng = np.random.default_rng(11)
+    cases = []
+    for lens in sorted(LENSES):
+        fnum, focal = LENSES[lens]
+        cases.append(dict(lensModel=1, lensDataPath=lens_path(lens), focalLength=float(np.float32(focal * rng.uniform(0.7, 1.5))),
+                          fStop=float(rng.choice([1.4, 2.0, 2.8, 5.6, 11.0])), focalDistance=float(np.float32(rng.uniform(20, 500))),
+                          kolbSamplingLUT=int(rng.integers(0, 2)), exposureControl=float(np.float32(rng.uniform(-2, 2)))))
+    for _ in range(4):
+        cases.append(dict(lensModel=0, focalLength=float(np.float32(rng.uniform(1.5, 8.0))), fStop=float(rng.choice([1.4, 2.8, 8.0])),
+                          focalDistance=float(np.float32(rng.uniform(20, 500))), useDof=int(rng.integers(0, 2)),
+                          opticalVignettingDistance=float(np.float32(rng.choice([0.0, 1.0, 3.0]))),
+                          opticalVignettingRadius=float(np.float32(rng.uniform(0.5, 2.0)))))
+    for k, kw in enumerate(cases):
+        r = ref.RefCamera(**kw)
+        p = port.PortCamera(**kw)
+        s = random_samples(2000, seed=100 + k)
+        o, d, st = r.generate(s, seed=k, first_index=1000 * k)
+        o2, d2, st2 = p.generate(s, seed=k, first_index=1000 * k, nthreads=2)
+        assert bits_equal(o, o2) and bits_equal(d, d2), kw
+        assert st["attempts"] == st2["attempts"], kw
+        r.close()
+        p.close()
