@@ -54,12 +54,13 @@ def _worker(rank, world, port_no, n, result_path):
     dist.destroy_process_group()
 
 
-def test_two_rank_sharding_and_gather_match_single_process(tmp_path):
+@pytest.mark.parametrize("n", [4001, 4000], ids=["ragged", "equal"])   # odd: the shards differ by one sample; even: the one-collective path
+def test_two_rank_sharding_and_gather_match_single_process(tmp_path, n):
     import torch.multiprocessing as mp
     from oracle import port
     from zoic_b200.workloads import config4
     from zutil import bits_equal
-    n, world = 4001, 2   # odd: the shards differ by one sample
+    world = 2
     out = str(tmp_path / "gathered.npz")
     mp.spawn(_worker, args=(world, _free_port(), n, out), nprocs=world, join=True)
     got = np.load(out)

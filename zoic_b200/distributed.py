@@ -25,6 +25,12 @@ def gather_rays(rays, group=None):
     counts = [int(c.item()) for c in counts]
     m = max(counts)
     width = rays.shape[1]
+    if min(counts) == m:
+        # equal shards (the usual case): one collective straight into the final buffer -- no per-rank staging tensors and
+        # no concatenation pass over the gathered records
+        full = torch.empty((world * m, width), dtype=rays.dtype, device=rays.device)
+        dist.all_gather_into_tensor(full, rays.contiguous(), group=group)
+        return full
     pad = rays if rays.shape[0] == m else torch.cat([rays, rays.new_zeros((m - rays.shape[0], width))])
     out = [torch.empty((m, width), dtype=rays.dtype, device=rays.device) for _ in range(world)]
     dist.all_gather(out, pad.contiguous(), group=group)
