@@ -355,6 +355,34 @@ def main():
         dist.all_reduce(tg, op=dist.ReduceOp.MAX)
         gather = {"value": world * m / (float(tg.item()) * 1e-3) / 1e6, "unit": UNIT, "rays_per_rank": m,
                   "what": "generate + all-gather of the 32-byte ray records to every rank (NCCL), max over ranks"}
+        # the same with double-buffered tiles: the gather of tile k travels while tile k+1 is generated
+        try:
+            from zoic_b200.distributed import TileGather
+            m2 = min(m, n // 2)
+            tiles = [rays[:m2], rays[m2:2 * m2]]
+            pipe = TileGather(m2, 8, torch.float32, dev)
+            reps = 6
+            for k in range(2):   # warm-up
+                pipe.wait(k & 1)
+                cam.create_rays(samples[:m2], seed=wl.seed, first_index=first, out=tiles[k & 1])
+                pipe.submit(k & 1, tiles[k & 1])
+            pipe.drain()
+            barrier()
+            g0.record()
+            for k in range(reps):
+                pipe.wait(k & 1)
+                cam.create_rays(samples[:m2], seed=wl.seed, first_index=first, out=tiles[k & 1])
+                pipe.submit(k & 1, tiles[k & 1])
+            pipe.drain()
+            g1.record()
+            barrier()
+            tp = torch.tensor([g0.elapsed_time(g1) / reps], dtype=torch.float64, device=dev)
+            dist.all_reduce(tp, op=dist.ReduceOp.MAX)
+            gather["pipelined"] = {"value": world * m2 / (float(tp.item()) * 1e-3) / 1e6, "unit": UNIT, "rays_per_rank": m2,
+                                   "what": "double-buffered tiles: all-gather of tile k overlaps the generation of tile k+1"}
+            del pipe
+        except Exception as exc:   # optional measurement: report, do not lose the bench line
+            gather["pipelined"] = {"error": repr(exc)}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:

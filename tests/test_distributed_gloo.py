@@ -92,3 +92,45 @@ def test_pass_major_shards_render_the_whole_film():
         for b in range(a + 1, world):
             assert not np.array_equal(shards[a], shards[b])
             assert len(set(map(bytes, shards[a])) & set(map(bytes, shards[b]))) == 0
+
+
+def _tile_worker(rank, world, port_no, result_path):
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import torch.distributed as dist
+    from zoic_b200.distributed import TileGather
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port_no)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rows, width, tiles = 257, 8, 5
+    g = TileGather(rows, width, torch.float32, torch.device("cpu"))
+    bufs = [torch.empty((rows, width)), torch.empty((rows, width))]
+    seen = []
+    for k in range(tiles):
+        b = k & 1
+        if k >= 2:
+            seen.append(g.wait(b).clone())   # tile k-2, gathered while tile k-1 was being produced
+        bufs[b].copy_(torch.arange(rows * width, dtype=torch.float32).reshape(rows, width) + 1000.0 * k + 100000.0 * rank)
+        g.submit(b, bufs[b])
+    order = [(tiles - 2) & 1, (tiles - 1) & 1]
+    for b in order:
+        seen.append(g.wait(b).clone())
+    if rank == 0:
+        np.save(result_path, torch.stack(seen).numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_double_buffered_tile_gather(tmp_path):
+    """TileGather: every tile arrives complete and in rank order although the next tile is written while it travels."""
+    import torch.multiprocessing as mp
+    out = str(tmp_path / "tiles.npy")
+    world = 2
+    mp.spawn(_tile_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    got = np.load(out)
+    rows, width, tiles = 257, 8, 5
+    assert got.shape == (tiles, world * rows, width)
+    base = np.arange(rows * width, dtype=np.float32).reshape(rows, width)
+    for k in range(tiles):
+        for r in range(world):
+            assert np.array_equal(got[k, r * rows:(r + 1) * rows], base + 1000.0 * k + 100000.0 * r)

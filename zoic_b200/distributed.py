@@ -45,3 +45,41 @@ def reduce_stats(stats, device, group=None):
     t = torch.tensor([stats[k] for k in keys], dtype=torch.int64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
     return {k: int(v) for k, v in zip(keys, t.tolist())}
+
+
+class TileGather:
+    """Double-buffered all-gather of finished ray tiles: the gather of tile k runs on the collective's
+    own stream / thread while tile k+1 is generated into the other tile buffer.  All ranks submit tiles of the same
+    shape.  Usage, with two tile buffers t[0], t[1]:
+
+        g = TileGather(rows, width, dtype, device)
+        for k in range(tiles):
+            b = k & 1
+            g.wait(b)                    # the gather that last read t[b] has finished: t[b] may be overwritten
+            generate(out=t[b])
+            g.submit(b, t[b])            # asynchronous; g.wait(b) later returns the gathered [world * rows, width] tile
+        g.drain()
+    """
+
+    def __init__(self, rows, width, dtype, device, group=None):
+        import torch
+        import torch.distributed as dist
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.full = [torch.empty((self.world * rows, width), dtype=dtype, device=device) for _ in range(2)]
+        self.work = [None, None]
+
+    def submit(self, b, tile):
+        import torch.distributed as dist
+        assert self.work[b] is None, "wait(b) before re-using buffer b"
+        self.work[b] = dist.all_gather_into_tensor(self.full[b], tile.contiguous(), group=self.group, async_op=True)
+
+    def wait(self, b):
+        """Blocks (stream-orders, on CUDA) until the gather submitted for buffer b is complete; returns the gathered tile."""
+        if self.work[b] is not None:
+            self.work[b].wait()
+            self.work[b] = None
+        return self.full[b]
+
+    def drain(self):
+        return [self.wait(0), self.wait(1)]
