@@ -33,9 +33,13 @@ def claim_stdout():
     so that whatever libraries print there (NCCL's version line, torchrun banners of child processes) cannot mix in."""
     global _JSON_FD
     if _JSON_FD is None:
-        sys.stdout.flush()
-        _JSON_FD = os.dup(1)
-        os.dup2(2, 1)
+        try:
+            sys.stdout.flush()
+            fd = os.dup(1)
+            os.dup2(2, 1)
+            _JSON_FD = fd
+        except OSError:   # no usable stdout / stderr descriptors: print the ordinary way
+            _JSON_FD = None
 
 
 def emit(line):
@@ -43,8 +47,10 @@ def emit(line):
     if _JSON_FD is None:
         sys.stdout.write(data.decode())
         sys.stdout.flush()
-    else:
-        os.write(_JSON_FD, data)
+        return
+    view = memoryview(data)
+    while len(view):
+        view = view[os.write(_JSON_FD, view):]
 
 
 def flops_per_batch(model, stats):
