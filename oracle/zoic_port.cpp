@@ -7,9 +7,9 @@
 //   * the exact number of attempts / lens-element visits per batch is known (roofline flop counts),
 //   * the CPU baseline can be timed on all host cores (the reference itself is not thread-safe).
 // PARITY PINNING: this restatement is checked bit-for-bit against the compiled, unmodified reference
-// (oracle/_ref, built by oracle/Makefile) in tests/test_oracle_port_vs_ref.py, and against the one
+// (oracle/_ref, built by oracle/Makefile) in tests/test_oracle_vs_reference.py, and against the one
 // externally authored known-answer test the reference holds (src/draw.zoic:1-10) in
-// tests/test_oracle_kat.py.  Golden vectors generated from the compiled reference are committed
+// tests/test_oracle_golden.py.  Golden vectors generated from the compiled reference are committed
 // under tests/golden/ so the pin also holds where /root/reference does not exist.
 //
 // Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may

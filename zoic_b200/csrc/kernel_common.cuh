@@ -125,7 +125,7 @@ __device__ __forceinline__ void lens_sample(const BokehView& b, float u, float v
 }
 
 // two draws of the per-sample stream; the FIRST draw feeds the SECOND parameter (g++ evaluates the
-// reference's argument lists right to left; pinned in tests/test_oracle_port_vs_ref.py)
+// reference's argument lists right to left; pinned in tests/test_oracle_golden.py::test_port_draw_order_matches_reference)
 __device__ __forceinline__ void draw_pair(Xor128& rng, float* first_param, float* second_param) {
     uint32_t k1 = xor128_next(rng);
     uint32_t k2 = xor128_next(rng);
