@@ -82,3 +82,32 @@ def test_null_arguments_are_rejected():
     assert lib.zoicb_get_stats(None, None) == capi.ERR_INVALID_ARGUMENT
     assert b"null" in lib.zoicb_last_error()
     assert lib.zoicb_version().startswith(b"zoicb")
+
+
+def test_a_plain_c_program_links_and_calls_the_library(tmp_path):
+    """include/zoicb.h + -lzoicb from C (no C++ or torch at the boundary).  Without a GPU the
+    program can still read the defaults, the version, and must be refused a context with ZOICB_ERR_CUDA."""
+    src = r'''
+    #include <stdio.h>
+    #include "zoicb.h"
+    int main(void) {
+        zoicb_params p; zoicb_default_params(&p);
+        zoicb_ctx* cam = 0;
+        p.lensModel = ZOICB_THINLENS;
+        int rc = zoicb_create(&p, 0, 0, 0, 0, 0, &cam);
+        printf("%s|%.1f|%d|%d|%s\n", zoicb_version(), p.focalLength, rc, cam != 0, rc ? zoicb_last_error() : "");
+        if (cam) zoicb_destroy(cam);
+        return 0;
+    }
+    '''
+    c = tmp_path / "t.c"
+    c.write_text(src)
+    exe = tmp_path / "t"
+    libdir = os.path.dirname(build.LIB)
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(c), "-o", str(exe), "-L", libdir, "-lzoicb",
+                    "-Wl,-rpath," + libdir], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.strip().split("|")
+    assert out[0].startswith("zoicb") and out[1] == "2.0"
+    import torch
+    if not torch.cuda.is_available():
+        assert int(out[2]) == capi.ERR_CUDA and out[3] == "0" and "no CUDA device" in out[4]
