@@ -239,3 +239,24 @@ def test_lens_table_grammar_fuzz(port, tmp_path):
             p.close()
             if not runs:
                 assert bits_equal(product_constants_flat(c)["lenses"], product_constants_flat(base)["lenses"]), (lens, variant)
+
+
+def test_bokeh_tables_random_images_with_ties(port):
+    """Seeded images of random shape with few grey levels (ties in every sort), zero borders and repeated rows: the host
+    statement of the table build equals the oracle's tables entry for entry (float bits, tie order included)."""
+    rng = np.random.default_rng(99)
+    for k in range(12):
+        h, w = int(rng.integers(2, 70)), int(rng.integers(2, 90))
+        levels = int(rng.choice([2, 3, 8, 64]))
+        img = (rng.integers(0, levels, (h, w, 1)) / max(1, levels - 1)).astype(np.float32).repeat(3, axis=2)
+        img[rng.random((h, w)) < 0.3] = 0.0
+        if h > 4:
+            img[1] = img[3]
+        img[0, 0] = 1.0   # never entirely black
+        kw = dict(lensModel=0, focalLength=3.5, fStop=2.8, useImage=1)
+        _, tabs = host_setup(image=img, **kw)
+        p = port.PortCamera(image=img, **kw)
+        for a, b in zip(tabs, p.bokeh_tables()):
+            assert a.dtype == b.dtype and np.array_equal(a.view(np.uint32) if a.dtype == np.float32 else a,
+                                                         b.view(np.uint32) if b.dtype == np.float32 else b), (k, h, w, levels)
+        p.close()
