@@ -14,6 +14,10 @@
  *   zoicb_transform_rays  (the renderer's camera-to-world step after camera_create_ray; nothing in zoic)
  *   zoicb_write_draw_file writeToFile + the DRAW_ONLY ray dumps  src/zoic.cpp:1240-1293, 1121-1128, 1146-1153
  *   zoicb_params        the 14 node parameters                   src/zoic.cpp:1547-1562
+ *   zoicb_run_job       the renderer's loop over camera_create_ray for a whole W x H x spp frame (nothing in zoic: Arnold
+ *                       calls src/zoic.cpp:1752-1990 once per sample), tile by tile through rotating device buffers
+ *   zoicb_gather_*      the final gather of the ray buffer to one GPU over NVLink (BASELINE north_star; nothing in zoic)
+ *   zoicb_census        GUARDED-vs-EXACT comparison of every record on the device (test / bench instrument)
  * The Arnold-shaped per-sample surface (NodeLoader + the six node callbacks, src/zoic.cpp:1999-2007)
  * is exported by the same library from zoic_b200/csrc/arnold_adapter.cpp on top of these calls.
  *
@@ -41,7 +45,7 @@ typedef enum zoicb_status {
     ZOICB_ERR_INVALID_ARGUMENT = 1,
     ZOICB_ERR_LENS_FILE = 2,      /* cannot open / parse the tabular lens file, bad column count   */
     ZOICB_ERR_LENS_DATA = 3,      /* more than one aperture stop, too many elements                */
-    ZOICB_ERR_BOKEH_IMAGE = 4,    /* useImage set but no usable pixels (needs >= 3 channels)       */
+    ZOICB_ERR_BOKEH_IMAGE = 4,    /* useImage set but no usable pixels                             */
     ZOICB_ERR_CUDA = 5,           /* no device, launch failure, allocation failure                 */
     ZOICB_ERR_UNSUPPORTED = 6
 } zoicb_status;
@@ -128,7 +132,10 @@ ZOICB_API void zoicb_default_params(zoicb_params* p);
 /* Build a camera on CUDA device `device`: parse params->lensDataPath, run the reference's setup pipeline
  * bit-exactly on the host (exit-pupil LUT traced on the GPU), build the bokeh row/column CDF tables from
  * `rgb` (row-major, channel-interleaved, height x width x nch floats; may be NULL unless useImage), and
- * upload everything.  The context is immutable afterwards, so generate calls are thread-safe. */
+ * upload everything.  An image with 1 or 2 channels is accepted the way the reference accepts it: as an INVALID image
+ * (imageData::isValid, src/zoic.cpp:135-137) whose every aperture sample is the lens centre (0, 0) (:420-425).
+ * The camera state is immutable afterwards and generate calls may come from several host threads: calls on one context
+ * serialise their (short) enqueue phase on an internal lock; kernels of different streams still overlap. */
 ZOICB_API zoicb_status zoicb_create(const zoicb_params* params, const float* rgb, int width, int height, int nch,
                           int device, zoicb_ctx** out);
 ZOICB_API void zoicb_destroy(zoicb_ctx* ctx);
@@ -182,6 +189,89 @@ ZOICB_API zoicb_status zoicb_transform_rays(zoicb_ctx* ctx, const zoicb_ray* d_r
 ZOICB_API zoicb_status zoicb_write_draw_file(zoicb_ctx* ctx, const char* path, const float* h_samples, uint32_t n,
                                              const uint64_t* h_indices, uint64_t first_index, uint64_t rng_seed);
 
+/* Wall time of zoicb_create's stages in milliseconds (each pointer may be NULL): the whole call, the exit-pupil LUT
+ * (3.2 M candidate rays classified and folded into 32 bounding boxes on the GPU; reference src/zoic.cpp:1391-1452),
+ * the image-based aperture tables (:222-417).  The reference spends 0.4-0.7 s in node_update on these. */
+ZOICB_API zoicb_status zoicb_get_create_times(const zoicb_ctx* ctx, double* total_ms, double* lut_ms, double* bokeh_ms);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Whole-frame jobs and the NVLink gather (section 8)
+ * ------------------------------------------------------------------------------------------------------------- */
+typedef struct zoicb_gather zoicb_gather;
+
+/* A job = the samples [first, first + count) of a synthetic W x H frame (zoicb_synth_samples with spp_per_pass samples
+ * per pixel and pass; the pixel index wraps once per pass, so a frame of P passes has W*H*spp_per_pass*P samples),
+ * generated tile by tile: synthesise on the device -> generate -> consume (a checksum kernel, the renderer's stand-in)
+ * through rotating buffers, three streams deep.  Jobs larger than HBM run at full size.  One GPU: first = 0, count =
+ * the frame.  G GPUs: rank r runs [r N/G, (r+1) N/G) -- whole passes, so every rank sees the whole film.
+ *   census      1: every tile is generated a second time in EXACT mode and all records are compared on the device
+ *   windows     records of n_windows index ranges [window_first[w], window_first[w] + window_count) (global sample
+ *               indices; the parts inside [first, first+count) are copied) -> d_windows[w * window_count ...] (device)
+ *   gather      NULL: every rank consumes its own tiles.  Otherwise the tiles of all ranks land in the consumer rank's
+ *               round buffers and are consumed there; gather_counts[world] = every rank's `count` (same array on all
+ *               ranks); `tile` is the gather's.  All ranks must call zoicb_run_job together.
+ *   serial      1: one stream, no overlap of the stages (A/B and debugging) */
+typedef struct zoicb_job {
+    uint32_t W, H, spp_per_pass;
+    int32_t census;
+    uint64_t sample_seed, rng_seed;
+    uint64_t first, count;
+    uint64_t tile;                  /* samples per tile, 0 = 2^27 */
+    float census_tol;               /* 0 = 1e-5 (north-star tolerance) */
+    int32_t n_windows;
+    const uint64_t* window_first;
+    uint64_t window_count;
+    zoicb_ray* d_windows;
+    zoicb_gather* gather;
+    const uint64_t* gather_counts;
+    int32_t serial;
+    int32_t reserved;
+} zoicb_job;
+
+typedef struct zoicb_job_result {
+    uint64_t rays, tiles, launches;
+    float device_ms;                /* CUDA-event time of the whole job (all stages, all streams joined)            */
+    float generate_ms;              /* sum of the generate kernels' own event times on their stream                 */
+    /* consumer totals (on the consumer rank of a gathered job: over the records of ALL ranks) */
+    uint64_t checksum;              /* order-independent: sum over records of sum_j word_j * K_j mod 2^64           */
+    uint64_t zero_weight, tries_sum, consumed;
+    /* census (GUARDED against EXACT, every record) */
+    uint64_t census_rays, census_flips, census_out_of_tol, census_live;
+    float census_max_rel_origin, census_max_dir;
+    zoicb_stats stats;              /* this job's counters (the context's running counters are not touched)         */
+    zoicb_stats census_stats;       /* the EXACT pass's counters                                                     */
+} zoicb_job_result;
+
+ZOICB_API zoicb_status zoicb_run_job(zoicb_ctx* ctx, const zoicb_job* job, zoicb_job_result* result);
+
+/* Compares n records of two device buffers (GUARDED output, EXACT output) like the census of zoicb_run_job and ADDS
+ * the totals to result's census_* fields.  Synchronises `stream`. */
+ZOICB_API zoicb_status zoicb_census(zoicb_ctx* ctx, const zoicb_ray* d_fast, const zoicb_ray* d_exact, uint64_t n, float tol,
+                                    zoicb_job_result* result, void* stream);
+
+/* Gather-to-consumer over NVLink, one process per GPU (zoic_b200/csrc/gather.cu).  Every rank contributes up to
+ * tile_rays records per round; the consumer rank owns `slots` round buffers of world x tile_rays records.
+ * Transports: FUSED -- the generate kernels store straight into the consumer's memory (CUDA IPC mapping; compute and
+ * transfer are one kernel); PUSH -- local staging tile + copy-engine push on a second stream; NCCL -- local staging tile +
+ * ncclSend / grouped ncclRecv (libnccl.so.2 is resolved at run time; none is needed for FUSED / PUSH).
+ * Set-up: create on every rank -> export a blob -> exchange the blobs by any means (torch.distributed, MPI, files) ->
+ * connect with all world blobs in rank order.  NCCL transport: instead (or as well) zoicb_gather_init_nccl with an id
+ * made by zoicb_nccl_unique_id on one rank, or zoicb_gather_use_nccl_comm with a communicator the caller owns. */
+enum { ZOICB_GATHER_FUSED = 1, ZOICB_GATHER_PUSH = 2, ZOICB_GATHER_NCCL = 3 };
+#define ZOICB_GATHER_BLOB_BYTES 192
+#define ZOICB_NCCL_ID_BYTES 128
+ZOICB_API zoicb_status zoicb_gather_create(int device, int rank, int world, int consumer, uint64_t tile_rays, int slots,
+                                           int transport, zoicb_gather** out);
+ZOICB_API zoicb_status zoicb_gather_export(zoicb_gather* g, void* blob /* ZOICB_GATHER_BLOB_BYTES */);
+ZOICB_API zoicb_status zoicb_gather_connect(zoicb_gather* g, const void* blobs /* world x ZOICB_GATHER_BLOB_BYTES */);
+ZOICB_API zoicb_status zoicb_nccl_unique_id(void* id /* ZOICB_NCCL_ID_BYTES */);
+ZOICB_API zoicb_status zoicb_gather_init_nccl(zoicb_gather* g, const void* id /* collective over all ranks */);
+ZOICB_API zoicb_status zoicb_gather_use_nccl_comm(zoicb_gather* g, void* nccl_comm /* an ncclComm_t */);
+/* Consumer rank only: copies n records of `rank`'s segment of round `round` of the LAST job (offset records in) to host
+ * memory -- valid while the round's slot has not been recycled (slots >= rounds keeps the whole job). */
+ZOICB_API zoicb_status zoicb_gather_read(zoicb_gather* g, uint64_t round, int rank, uint64_t offset, uint64_t n, zoicb_ray* h_out);
+ZOICB_API void zoicb_gather_destroy(zoicb_gather* g);
+
 /* Synthetic camera samples for benchmarks and parity tests: sample index i is
  * pixel-major / spp-minor over a W x H image, four 24-bit uniforms from a counter hash of (seed, i). */
 ZOICB_API zoicb_status zoicb_synth_samples(zoicb_ctx* ctx, uint32_t W, uint32_t H, uint32_t spp, uint64_t seed,
@@ -215,6 +305,13 @@ ZOICB_API zoicb_status zoicb_build_bokeh_tables(int device, const float* rgb, in
  * std::sort the device code uses (csrc/gnu_sort.h) into `restated`, and with the toolchain's own std::sort and the
  * reference's comparator shape (src/zoic.cpp:317) into `library` -- so a test can show the two agree, ties included. */
 ZOICB_API zoicb_status zoicb_debug_sort_orders(const float* values, int32_t n, int32_t* restated, int32_t* library);
+
+/* Test hook: folds candidate points into the exit-pupil LUT's bounding boxes the way the reference does (in order, with
+ * the re-arm quirk of src/zoic.cpp:1423) -- on the GPU (lut_bbox_kernel, what zoicb_create runs) into boxes_device and
+ * with the host statement into boxes_host (either may be NULL).  draws: n_film x per_film pairs of xor128 outputs,
+ * accept: n_film x per_film flags, boxes: n_film x (min.x, min.y, max.x, max.y). */
+ZOICB_API zoicb_status zoicb_debug_lut_boxes(int device, const uint32_t* draws, const uint8_t* accept, int32_t n_film,
+                                             int32_t per_film, float first_aperture, float* boxes_device, float* boxes_host);
 
 /* Measured fp32 FMA throughput of the device (dependent-chain-free FFMA kernel), in TFLOP/s: the
  * denominator of the fp32 roofline that bench.py reports. */

@@ -43,7 +43,7 @@ def _worker(rank, world, port_no, n, result_path):
     wl = config4()
     first, count = shard_range(n, rank, world)
     base = 3_000_000_000  # a window in the middle of the 7680x4320x128 grid
-    s = port.synth_samples(wl.W, wl.H, wl.spp, wl.seed, base + first, count)
+    s = port.synth_samples(*wl.synth_args(), base + first, count)
     cam = port.PortCamera(**wl.params)
     o, d, st = cam.generate(s, seed=wl.seed, first_index=base + first)
     g = gather_rays(torch.from_numpy(np.concatenate([o, d], axis=1)))
@@ -66,7 +66,7 @@ def test_two_rank_sharding_and_gather_match_single_process(tmp_path, n):
     got = np.load(out)
     wl = config4()
     base = 3_000_000_000
-    s = port.synth_samples(wl.W, wl.H, wl.spp, wl.seed, base, n)
+    s = port.synth_samples(*wl.synth_args(), base, n)
     cam = port.PortCamera(**wl.params)
     o, d, st = cam.generate(s, seed=wl.seed, first_index=base)
     assert bits_equal(got["o"], o) and bits_equal(got["d"], d)
@@ -74,63 +74,70 @@ def test_two_rank_sharding_and_gather_match_single_process(tmp_path, n):
 
 
 def test_pass_major_shards_render_the_whole_film():
-    """bench.py's layout: rank r owns samples [r*n, (r+1)*n) of a W x H x spp job repeated
-    `world` times, n = W*H*spp.  The pixel of sample i wraps per pass, so every rank covers every pixel with its
-    own spp samples -- the same work mix on every rank -- and no two ranks share a sample."""
+    """The frame layout (zoic_b200.workloads): a W x H x spp frame in 8 passes of spp / 8 samples per
+    pixel; rank r of G owns passes [r 8/G, (r+1) 8/G) = samples [r N/G, (r+1) N/G).  The pixel of sample i wraps per pass,
+    so every rank covers every pixel with its own samples -- the same work mix on every rank --, no two ranks share a
+    sample, and the union over the ranks is the same sample set for every G."""
     from oracle import port
+    from zoic_b200.distributed import job_share
     port.load()
-    W, H, spp, world, seed = 12, 8, 4, 3, 77
+    W, H, spp, passes, seed = 12, 8, 16, 8, 77
     n = W * H * spp
-    shards = [port.synth_samples(W, H, spp, seed, r * n, n) for r in range(world)]
-    for s in shards:
-        px = np.floor((s[:, 0] + 1.0) * 0.5 * W).astype(int)
-        py = np.floor((1.0 - s[:, 1] * (W / H)) * 0.5 * H).astype(int)
-        counts = np.zeros((H, W), int)
-        np.add.at(counts, (np.clip(py, 0, H - 1), np.clip(px, 0, W - 1)), 1)
-        assert (counts == spp).all()          # every pixel, spp samples each
-    for a in range(world):
-        for b in range(a + 1, world):
-            assert not np.array_equal(shards[a], shards[b])
-            assert len(set(map(bytes, shards[a])) & set(map(bytes, shards[b]))) == 0
+    whole = port.synth_samples(W, H, spp // passes, seed, 0, n)
+    for world in (1, 2, 4, 8):
+        shards = []
+        for r in range(world):
+            first, count = job_share(n, passes, r, world)
+            assert first == r * n // world and count == n // world
+            shards.append(port.synth_samples(W, H, spp // passes, seed, first, count))
+        for s in shards:
+            px = np.floor((s[:, 0] + 1.0) * 0.5 * W).astype(int)
+            py = np.floor((1.0 - s[:, 1] * (W / H)) * 0.5 * H).astype(int)
+            counts = np.zeros((H, W), int)
+            np.add.at(counts, (np.clip(py, 0, H - 1), np.clip(px, 0, W - 1)), 1)
+            assert (counts == spp // world).all()          # every pixel, spp / world samples each
+        assert np.array_equal(np.concatenate(shards), whole)   # the same job for every world size
+    with pytest.raises(ValueError):
+        job_share(n, passes, 0, 3)
 
 
-def _tile_worker(rank, world, port_no, result_path):
+def _share_worker(rank, world, port_no, result_path):
     import sys
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     import torch.distributed as dist
-    from zoic_b200.distributed import TileGather
+    from oracle import port
+    from zoic_b200.distributed import gather_rays, job_share, reduce_stats
+    from zoic_b200.workloads import Workload, _kolb
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port_no)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    rows, width, tiles = 257, 8, 5
-    g = TileGather(rows, width, torch.float32, torch.device("cpu"))
-    bufs = [torch.empty((rows, width)), torch.empty((rows, width))]
-    seen = []
-    for k in range(tiles):
-        b = k & 1
-        if k >= 2:
-            seen.append(g.wait(b).clone())   # tile k-2, gathered while tile k-1 was being produced
-        bufs[b].copy_(torch.arange(rows * width, dtype=torch.float32).reshape(rows, width) + 1000.0 * k + 100000.0 * rank)
-        g.submit(b, bufs[b])
-    order = [(tiles - 2) & 1, (tiles - 1) & 1]
-    for b in order:
-        seen.append(g.wait(b).clone())
+    wl = Workload("tiny double gauss", 16, 9, 16, 5, _kolb("double_gauss_f2.0.dat", 5.0, 2.0))
+    first, count = job_share(wl.n, wl.passes, rank, world)
+    s = port.synth_samples(*wl.synth_args(), first, count)
+    cam = port.PortCamera(**wl.params)
+    o, d, st = cam.generate(s, seed=wl.seed, first_index=first)
+    g = gather_rays(torch.from_numpy(np.concatenate([o, d], axis=1)))
+    total = reduce_stats(st, torch.device("cpu"))
     if rank == 0:
-        np.save(result_path, torch.stack(seen).numpy())
+        np.savez(result_path, rays=g.numpy(), stats=np.array([total[k] for k in sorted(total)]))
     dist.barrier()
     dist.destroy_process_group()
 
 
-def test_double_buffered_tile_gather(tmp_path):
-    """TileGather: every tile arrives complete and in rank order although the next tile is written while it travels."""
+def test_strong_split_of_a_frame_equals_the_single_process_job(tmp_path):
+    """bench.py's multi-GPU job on CPU: two ranks take their job_share of one small frame (the oracle standing in for the
+    kernels), the gathered records and the summed counters equal the whole frame generated by one process, bit for bit."""
     import torch.multiprocessing as mp
-    out = str(tmp_path / "tiles.npy")
+    from oracle import port
+    from zoic_b200.workloads import Workload, _kolb
+    from zutil import bits_equal
     world = 2
-    mp.spawn(_tile_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    out = str(tmp_path / "frame.npz")
+    mp.spawn(_share_worker, args=(world, _free_port(), out), nprocs=world, join=True)
     got = np.load(out)
-    rows, width, tiles = 257, 8, 5
-    assert got.shape == (tiles, world * rows, width)
-    base = np.arange(rows * width, dtype=np.float32).reshape(rows, width)
-    for k in range(tiles):
-        for r in range(world):
-            assert np.array_equal(got[k, r * rows:(r + 1) * rows], base + 1000.0 * k + 100000.0 * r)
+    wl = Workload("tiny double gauss", 16, 9, 16, 5, _kolb("double_gauss_f2.0.dat", 5.0, 2.0))
+    s = port.synth_samples(*wl.synth_args(), 0, wl.n)
+    cam = port.PortCamera(**wl.params)
+    o, d, st = cam.generate(s, seed=wl.seed, first_index=0)
+    assert bits_equal(got["rays"], np.concatenate([o, d], axis=1))
+    assert list(got["stats"]) == [st[k] for k in sorted(st)]

@@ -91,6 +91,19 @@ def test_kolb_lut_hex_bokeh(port):
                       useImage=1), port, n=60_000, image=hex_bokeh_image(255))
 
 
+@pytest.mark.parametrize("nch", [1, 2])
+def test_bokeh_image_with_fewer_than_three_channels(port, nch):
+    """A 1- or 2-channel image is what it is in the reference: accepted, invalid (src/zoic.cpp:135-137), every aperture
+    sample the lens centre (:420-425) -- pinned against the compiled reference in tests/test_oracle_vs_reference.py."""
+    from zoic_b200.workloads import lens_path
+    img = np.random.default_rng(nch).random((9, 7, nch)).astype(np.float32)
+    _check_exact(dict(lensModel=0, focalLength=3.5, fStop=2.8, opticalVignettingDistance=2.0, useImage=1), port, n=50_000, image=img)
+    _check_exact(dict(lensModel=1, lensDataPath=lens_path("double_gauss_f2.0.dat"), focalLength=5.0, fStop=2.0, useImage=1),
+                 port, n=50_000, image=img)
+    _check_guarded(dict(lensModel=1, lensDataPath=lens_path("double_gauss_f2.0.dat"), focalLength=5.0, fStop=2.0, useImage=1),
+                   port, n=100_000, image=img)
+
+
 def test_synth_samples_match_oracle(port):
     from zoic_b200 import ZoicCamera
     cam = ZoicCamera(lensModel=0, focalLength=3.5, fStop=2.8)
@@ -330,7 +343,7 @@ def test_large_batch_spans_many_chunks_and_keeps_counters(port):
     wl = config4()
     cam = ZoicCamera(**wl.params)
     n = 1 << 22
-    s = cam.synth_samples(wl.W, wl.H, wl.spp, wl.seed, 0, n)
+    s = cam.synth_samples(*wl.synth_args(), 0, n)
     rays = torch.full((n, 8), float("nan"), device="cuda")
     cam.reset_stats()
     cam.create_rays(s, seed=wl.seed, first_index=0, out=rays)
@@ -392,7 +405,7 @@ def test_camera_to_world_epilogue_matches_the_contract(port):
     wl = config2()
     cam = ZoicCamera(**wl.params)
     n = 300_001   # not a multiple of anything
-    s = cam.synth_samples(wl.W, wl.H, wl.spp, wl.seed, 5_000_000, n)
+    s = cam.synth_samples(*wl.synth_args(), 5_000_000, n)
     rays = cam.create_rays(s, seed=wl.seed, first_index=5_000_000)
     torch.cuda.synchronize()
     host = rays.cpu().numpy()
@@ -425,10 +438,10 @@ def test_camera_to_world_epilogue_matches_the_contract(port):
     cam.close()
 
 
-@pytest.mark.parametrize("pool", ["1", "2"])
-def test_both_pool_kernels_on_every_lens(pool):
-    """The host picks the scalar or the packed pool kernel per camera; ZOICB_POOL=1 / 2 forces one of them (read once
-    per process), so the all-lenses and bokeh parity tests run again in a child process for each."""
+@pytest.mark.parametrize("pool", ["2", "3"])
+def test_both_pool_flavours_on_every_lens(pool):
+    """The host picks the plain or the rim pre-test flavour of the pool kernel per camera; ZOICB_POOL=2 / 3 forces one of
+    them (read once per process), so the all-lenses and bokeh parity tests run again in a child process for each."""
     import os
     import subprocess
     import sys
@@ -553,7 +566,7 @@ def test_full_size_batches_hold_the_invariants(port, name):
     tile = 1 << 27
     for b in range(0, n, tile):
         m = min(tile, n - b)
-        cam.synth_samples(wl.W, wl.H, wl.spp, wl.seed, b, m, out=s[b:b + m])
+        cam.synth_samples(*wl.synth_args(), b, m, out=s[b:b + m])
     rays = torch.full((n, 8), float("nan"), device="cuda")
     cam.reset_stats()
     cam.create_rays(s, seed=wl.seed, first_index=0, out=rays)

@@ -163,9 +163,9 @@ def test_error_codes(tmp_path):
     with pytest.raises(capi.ZoicError) as e:
         host_setup(lensModel=0, useImage=1)
     assert e.value.code == capi.ERR_BOKEH_IMAGE
-    with pytest.raises(capi.ZoicError) as e:
-        host_setup(lensModel=0, useImage=1, image=np.ones((4, 4, 2), np.float32))
-    assert e.value.code == capi.ERR_BOKEH_IMAGE
+    # 1 or 2 channels: accepted like the reference accepts them -- as an invalid image without tables (src/zoic.cpp:135-137)
+    c, tabs = host_setup(lensModel=0, useImage=1, image=np.ones((4, 5, 2), np.float32))
+    assert c["bokehWidth"] == 5 and c["bokehHeight"] == 4 and all(not t.any() for t in tabs)
     with pytest.raises(capi.ZoicError) as e:
         host_setup(lensModel=7)
     assert e.value.code == capi.ERR_INVALID_ARGUMENT

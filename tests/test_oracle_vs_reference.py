@@ -55,6 +55,28 @@ def test_port_equals_compiled_reference(port, name, kw, img, n):
     p.close()
 
 
+@pytest.mark.parametrize("nch", [1, 2])
+def test_image_with_fewer_than_three_channels_is_the_lens_centre(port, nch):
+    """The reference reads a 1- or 2-channel bokeh image without complaint but imageData::isValid() wants >= 3 channels
+    (src/zoic.cpp:135-137): no tables are built and every bokehSample answers (0, 0) (:420-425).  Restatement and compiled
+    reference agree bit for bit -- this is the behaviour the product keeps (tests/test_gpu_parity.py)."""
+    ref = _ref()
+    from zoic_b200.workloads import lens_path
+    img = np.random.default_rng(nch).random((9, 7, nch)).astype(np.float32)
+    for kw in (dict(lensModel=0, focalLength=3.5, fStop=2.8, opticalVignettingDistance=2.0, useImage=1),
+               dict(lensModel=1, lensDataPath=lens_path("double_gauss_f2.0.dat"), focalLength=5.0, fStop=2.0, useImage=1)):
+        r = ref.RefCamera(image=img, **kw)
+        p = port.PortCamera(image=img, **kw)
+        s = random_samples(5_000, seed=nch)
+        o, d, st = r.generate(s, seed=3, first_index=0)
+        o2, d2, st2 = p.generate(s, seed=3, first_index=0)
+        assert bits_equal(o, o2) and bits_equal(d, d2) and st["attempts"] == st2["attempts"]
+        if kw["lensModel"] == 0:
+            assert not o2[:, :3].any()          # thin lens: every ray leaves the lens centre
+        r.close()
+        p.close()
+
+
 def test_plugin_surface_of_the_reference():
     """NodeLoader contract (reference src/zoic.cpp:1999-2007): one node, named "zoic", camera type."""
     ref = _ref()

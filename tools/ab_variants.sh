@@ -13,10 +13,3 @@ except Exception as e: print('$v $wl FAILED', e)
 "
   done
 done
-# the scalar (one ray per lane) pool kernel of the main library, same sizes
-for wl in headline config4; do
-  spp=32; [ $wl = config4 ] && spp=8
-  ZOICB_POOL=1 python bench.py --workload $wl --spp $spp --steps 5 --warmup 3 --no-cpu --no-e2e 2>&1 | python -c "
-import json,sys
-d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('scalar $wl', round(d['value']), 'Mrays/s', round(d['ms_per_step'],2), 'ms')"
-done

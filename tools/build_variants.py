@@ -24,7 +24,7 @@ def one(src, name, flags):
     if r.returncode: return name, r.stdout + r.stderr
     base = os.path.join(ROOT, "zoic_b200", "lib", "obj")
     objs = [os.path.join(base, s + ".o") for s in zb.SOURCES if s != src] + [obj]
-    subprocess.check_call([zb._nvcc()] + cc + zb.ARCH + ["-shared", "-o", os.path.join(out, "libzoicb.so")] + objs + ["-lpthread"])
+    subprocess.check_call([zb._nvcc()] + cc + zb.ARCH + ["-shared", "-o", os.path.join(out, "libzoicb.so")] + objs + ["-lpthread", "-ldl"])
     plug = os.path.join(ROOT, "zoic_b200", "lib", "libzoic_arnold.so")
     if os.path.exists(plug): shutil.copy(plug, out)
     return name, (r.stdout + r.stderr).strip()

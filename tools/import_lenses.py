@@ -4,7 +4,8 @@ The prescriptions are published optical designs (radius, thickness, index, [V-nu
 surface, millimetres, front surface first).  This script reads the numeric fields of each table under
 <reference>/lenses_tabular and writes them, numeric token for numeric token, to zoic_b200/data/lenses/ with
 this repository's header, so that the GPU box (which has no reference tree) can run every configuration.
-tests/test_lens_data.py checks that both spellings parse to identical element tables.
+tests/test_host_setup.py::test_shipped_lens_tables_parse_like_the_reference_originals checks that both spellings parse to
+identical element tables.
 
 usage: python tools/import_lenses.py [/root/reference]
 """

@@ -30,7 +30,7 @@ def compare(o, d, oe, de, tol=1e-5):
 
 def run(name, wl, n, first, scales):
     cam = ZoicCamera(image=wl.image(), **wl.params)
-    s = cam.synth_samples(wl.W, wl.H, wl.spp, wl.seed, first, n)
+    s = cam.synth_samples(*wl.synth_args(), first, n)
     cam.set_mode(MODE_EXACT)
     cam.reset_stats()
     re_ = cam.create_rays(s, seed=wl.seed, first_index=first)

@@ -4,4 +4,5 @@ Only what the hot path needs lives here: csrc/ (CUDA kernels, host setup, the C 
 adapter), the ctypes binding (capi), the host-side mirror of the camera node (camera) and synthetic
 workloads (synth).
 """
-from .camera import ZoicCamera, build_bokeh_tables, host_setup, make_params, split_rays, THINLENS, RAYTRACED, MODE_EXACT, MODE_GUARDED  # noqa: F401
+from .camera import (ZoicCamera, Gather, build_bokeh_tables, debug_lut_boxes, host_setup, make_params, nccl_unique_id,  # noqa: F401
+                     split_rays, THINLENS, RAYTRACED, MODE_EXACT, MODE_GUARDED)

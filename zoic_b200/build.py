@@ -14,10 +14,11 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.environ.get("ZOICB_LIBDIR") or os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libzoicb.so")
 
-SOURCES = ["capi.cu", "kernels.cu", "kolb_pool.cu", "kolb_pool2.cu", "bokeh_build.cu", "host_setup.cpp"]
+SOURCES = ["capi.cu", "kernels.cu", "kolb_pool2.cu", "bokeh_build.cu", "job.cu", "gather.cu", "host_setup.cpp"]
 ADAPTER = "arnold_adapter.cpp"
 PLUGIN = os.path.join(LIBDIR, "libzoic_arnold.so")
 HEADERS = ["camera_state.h", "lens_math.cuh", "host_setup.h", "kernels.h", "kernel_common.cuh", "gnu_sort.h",
+           "capi_internal.h", "gather.h",
            os.path.join(ROOT, "include", "zoicb.h"), os.path.join(ROOT, "include", "arnold_shim", "ai.h")]
 
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
@@ -68,7 +69,7 @@ def build_library(force=False, verbose=False):
         failed |= p.returncode != 0
     if failed:
         raise RuntimeError("nvcc failed")
-    link = [_nvcc()] + ccbin + ARCH + ["-shared", "-o", LIB] + objs + ["-lpthread"]
+    link = [_nvcc()] + ccbin + ARCH + ["-shared", "-o", LIB] + objs + ["-lpthread", "-ldl"]
     subprocess.check_call(link)
     # the Arnold-shaped plugin: NodeLoader + node callbacks on top of libzoicb.so; the Ai* host functions stay
     # undefined and are resolved by the host application (Arnold, or the test host) at load time

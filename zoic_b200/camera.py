@@ -151,12 +151,33 @@ class ZoicCamera:
         return out
 
     def create_rays_host(self, samples, seed=0, first_index=0, out=None):
-        """The same for HOST memory (numpy arrays or CPU tensors; pinned memory is copied directly)."""
+        """The same for HOST memory (numpy arrays or CPU tensors; pinned memory is copied directly): samples [n, 4]
+        float32 C-contiguous, out [n, 8] float32 C-contiguous.  numpy input of another dtype / layout is converted (a copy);
+        tensors and `out` must already have the right layout."""
+        def is_tensor(a):
+            return hasattr(a, "data_ptr")
+
+        def check(a, what, width):
+            if is_tensor(a):
+                import torch
+                ok = (not a.is_cuda) and a.dtype == torch.float32 and a.is_contiguous() and a.numel() % width == 0
+            else:
+                ok = isinstance(a, np.ndarray) and a.dtype == np.float32 and a.flags["C_CONTIGUOUS"] and a.size % width == 0
+            if not ok:
+                raise TypeError("%s must be a C-contiguous float32 host array with a multiple of %d elements" % (what, width))
+
+        if not is_tensor(samples):
+            samples = np.ascontiguousarray(samples, dtype=np.float32)
+        check(samples, "samples", 4)
+
         def ptr(a):
-            return a.data_ptr() if hasattr(a, "data_ptr") else a.ctypes.data
-        n = (samples.numel() if hasattr(samples, "numel") else samples.size) // 4
+            return a.data_ptr() if is_tensor(a) else a.ctypes.data
+        n = (samples.numel() if is_tensor(samples) else samples.size) // 4
         if out is None:
             out = np.empty((n, 8), np.float32)
+        check(out, "out", 8)
+        if (out.numel() if is_tensor(out) else out.size) != 8 * n:
+            raise ValueError("out must hold 8 floats per sample")
         capi.check(self.lib.zoicb_generate_host(self.ctx, ptr(samples), n, first_index, seed, ptr(out)))
         return out
 
@@ -196,6 +217,60 @@ class ZoicCamera:
                                                 C.c_void_p(stream)))
         return out
 
+    # -- whole-frame jobs -------------------------------------------------------------------------
+    def run_job(self, W, H, spp_per_pass, sample_seed, rng_seed, first, count, tile=0, census=False, census_tol=0.0,
+                windows=None, window_count=0, gather=None, gather_counts=None, serial=False):
+        """zoicb_run_job: the samples [first, first + count) of a synthetic W x H frame, tile by tile through rotating
+        device buffers (synthesise -> generate -> consume), optionally with the GUARDED-vs-EXACT census of every record,
+        windows of records copied out for the oracle, and the NVLink gather to a consumer rank.
+        Returns a dict of the result fields; with `windows` (a list of global sample indices) also "windows": a CUDA
+        tensor [len(windows), window_count, 8]."""
+        import torch
+        job = capi.Job()
+        job.W, job.H, job.spp_per_pass = int(W), int(H), int(spp_per_pass)
+        job.sample_seed, job.rng_seed, job.first, job.count = int(sample_seed), int(rng_seed), int(first), int(count)
+        job.tile, job.census, job.census_tol, job.serial = int(tile), int(bool(census)), float(census_tol), int(bool(serial))
+        keep = []
+        wout = None
+        if windows:
+            wf = np.ascontiguousarray(windows, dtype=np.uint64)
+            wout = torch.full((len(wf), int(window_count), 8), float("nan"), dtype=torch.float32,
+                              device=torch.device("cuda", self.device))
+            job.n_windows, job.window_first, job.window_count, job.d_windows = len(wf), wf.ctypes.data, int(window_count), wout.data_ptr()
+            keep.append(wf)
+        if gather is not None:
+            gc = np.ascontiguousarray(gather_counts, dtype=np.uint64)
+            assert len(gc) == gather.world
+            job.gather, job.gather_counts = gather.handle, gc.ctypes.data
+            keep.append(gc)
+        res = capi.JobResult()
+        capi.check(self.lib.zoicb_run_job(self.ctx, C.byref(job), C.byref(res)))
+        out = {k: getattr(res, k) for k, _ in capi.JobResult._fields_ if k not in ("stats", "census_stats")}
+        out["stats"] = {k: int(getattr(res.stats, k)) for k, _ in capi.Stats._fields_}
+        out["census_stats"] = {k: int(getattr(res.census_stats, k)) for k, _ in capi.Stats._fields_}
+        if wout is not None:
+            out["windows"] = wout
+        return out
+
+    def census(self, fast, exact, tol=1e-5, stream=None):
+        """GUARDED-vs-EXACT comparison of two resident ray buffers on the device (zoicb_census)."""
+        import torch
+        assert fast.is_cuda and exact.is_cuda and fast.dtype == exact.dtype == torch.float32
+        assert fast.is_contiguous() and exact.is_contiguous() and fast.numel() == exact.numel()
+        if stream is None:
+            stream = torch.cuda.current_stream(fast.device).cuda_stream
+        res = capi.JobResult()
+        capi.check(self.lib.zoicb_census(self.ctx, fast.data_ptr(), exact.data_ptr(), fast.numel() // 8, float(tol),
+                                         C.byref(res), C.c_void_p(stream)))
+        return {"rays": res.census_rays, "flips": res.census_flips, "out_of_tol": res.census_out_of_tol,
+                "live": res.census_live, "max_rel_origin": res.census_max_rel_origin, "max_dir": res.census_max_dir}
+
+    def create_times(self):
+        """Milliseconds zoicb_create spent: whole call, exit-pupil LUT, image-based aperture tables."""
+        t, l, b = C.c_double(0), C.c_double(0), C.c_double(0)
+        capi.check(self.lib.zoicb_get_create_times(self.ctx, C.byref(t), C.byref(l), C.byref(b)))
+        return {"create_ms": t.value, "lut_ms": l.value, "bokeh_ms": b.value}
+
     def stats(self):
         s = capi.Stats()
         capi.check(self.lib.zoicb_get_stats(self.ctx, C.byref(s)))
@@ -214,6 +289,72 @@ class ZoicCamera:
             self.close()
         except Exception:
             pass
+
+
+class Gather:
+    """zoicb_gather: gather-to-consumer of ray tiles over NVLink, one process per GPU (zoic_b200/csrc/gather.cu).
+    Set-up is collective: every rank creates, exports its blob, the blobs are exchanged (zoic_b200.distributed
+    .connect_gather does it over torch.distributed) and every rank connects."""
+
+    TRANSPORTS = {"fused": capi.GATHER_FUSED, "push": capi.GATHER_PUSH, "nccl": capi.GATHER_NCCL}
+
+    def __init__(self, device, rank, world, consumer, tile_rays, slots=2, transport="fused"):
+        self.lib = capi.load()
+        self.rank, self.world, self.consumer, self.tile, self.slots = int(rank), int(world), int(consumer), int(tile_rays), int(slots)
+        self.transport = transport
+        h = C.c_void_p()
+        capi.check(self.lib.zoicb_gather_create(int(device), self.rank, self.world, self.consumer, self.tile, self.slots,
+                                                self.TRANSPORTS[transport], C.byref(h)))
+        self.handle = h
+
+    def export(self):
+        buf = C.create_string_buffer(capi.GATHER_BLOB_BYTES)
+        capi.check(self.lib.zoicb_gather_export(self.handle, buf))
+        return buf.raw
+
+    def connect(self, blobs):
+        joined = b"".join(blobs)
+        assert len(joined) == self.world * capi.GATHER_BLOB_BYTES
+        capi.check(self.lib.zoicb_gather_connect(self.handle, joined))
+
+    def init_nccl(self, unique_id):
+        capi.check(self.lib.zoicb_gather_init_nccl(self.handle, unique_id))
+
+    def read(self, round_, rank, offset, n):
+        out = np.empty((n, 8), np.float32)
+        capi.check(self.lib.zoicb_gather_read(self.handle, int(round_), int(rank), int(offset), int(n), out.ctypes.data))
+        return out
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.zoicb_gather_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def nccl_unique_id():
+    buf = C.create_string_buffer(capi.NCCL_ID_BYTES)
+    capi.check(capi.load().zoicb_nccl_unique_id(buf))
+    return buf.raw
+
+
+def debug_lut_boxes(draws, accept, n_film, per_film, first_aperture, device=None):
+    """(boxes_device or None, boxes_host): the exit-pupil LUT's bounding-box fold (reference src/zoic.cpp:1421-1440)
+    on the GPU and by the host statement, for given candidate draws / accept flags."""
+    d = np.ascontiguousarray(draws, np.uint32).reshape(-1)
+    a = np.ascontiguousarray(accept, np.uint8).reshape(-1)
+    assert len(d) == 2 * n_film * per_film and len(a) == n_film * per_film
+    host = np.zeros((n_film, 4), np.float32)
+    dev = np.zeros((n_film, 4), np.float32) if device is not None else None
+    capi.check(capi.load().zoicb_debug_lut_boxes(int(device or 0), d.ctypes.data, a.ctypes.data, n_film, per_film,
+                                                 float(first_aperture), None if dev is None else dev.ctypes.data,
+                                                 host.ctypes.data))
+    return dev, host
 
 
 def split_rays(rays):

@@ -51,6 +51,31 @@ class Constants(C.Structure):
     ]
 
 
+class Job(C.Structure):
+    """zoicb_job: a range of a synthetic W x H frame, generated tile by tile (include/zoicb.h)."""
+    _fields_ = [
+        ("W", C.c_uint32), ("H", C.c_uint32), ("spp_per_pass", C.c_uint32), ("census", C.c_int32),
+        ("sample_seed", C.c_uint64), ("rng_seed", C.c_uint64), ("first", C.c_uint64), ("count", C.c_uint64),
+        ("tile", C.c_uint64), ("census_tol", C.c_float), ("n_windows", C.c_int32),
+        ("window_first", C.c_void_p), ("window_count", C.c_uint64), ("d_windows", C.c_void_p),
+        ("gather", C.c_void_p), ("gather_counts", C.c_void_p), ("serial", C.c_int32), ("reserved", C.c_int32),
+    ]
+
+
+class JobResult(C.Structure):
+    _fields_ = [
+        ("rays", C.c_uint64), ("tiles", C.c_uint64), ("launches", C.c_uint64),
+        ("device_ms", C.c_float), ("generate_ms", C.c_float),
+        ("checksum", C.c_uint64), ("zero_weight", C.c_uint64), ("tries_sum", C.c_uint64), ("consumed", C.c_uint64),
+        ("census_rays", C.c_uint64), ("census_flips", C.c_uint64), ("census_out_of_tol", C.c_uint64),
+        ("census_live", C.c_uint64), ("census_max_rel_origin", C.c_float), ("census_max_dir", C.c_float),
+        ("stats", Stats), ("census_stats", Stats),
+    ]
+
+
+GATHER_FUSED, GATHER_PUSH, GATHER_NCCL = 1, 2, 3
+GATHER_BLOB_BYTES, NCCL_ID_BYTES = 192, 128
+
 # every symbol include/zoicb.h declares: name -> (restype, argtypes)
 _P = C.c_void_p
 SYMBOLS = {
@@ -74,6 +99,18 @@ SYMBOLS = {
     "zoicb_build_bokeh_tables": (C.c_int, [C.c_int, _P, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, C.POINTER(C.c_float)]),
     "zoicb_debug_sort_orders": (C.c_int, [_P, C.c_int32, _P, _P]),
     "zoicb_measure_fp32_peak": (C.c_int, [C.c_int, C.POINTER(C.c_double)]),
+    "zoicb_get_create_times": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "zoicb_debug_lut_boxes": (C.c_int, [C.c_int, _P, _P, C.c_int32, C.c_int32, C.c_float, _P, _P]),
+    "zoicb_run_job": (C.c_int, [_P, C.POINTER(Job), C.POINTER(JobResult)]),
+    "zoicb_census": (C.c_int, [_P, _P, _P, C.c_uint64, C.c_float, C.POINTER(JobResult), _P]),
+    "zoicb_gather_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_int, C.c_int, C.POINTER(_P)]),
+    "zoicb_gather_export": (C.c_int, [_P, _P]),
+    "zoicb_gather_connect": (C.c_int, [_P, _P]),
+    "zoicb_nccl_unique_id": (C.c_int, [_P]),
+    "zoicb_gather_init_nccl": (C.c_int, [_P, _P]),
+    "zoicb_gather_use_nccl_comm": (C.c_int, [_P, _P]),
+    "zoicb_gather_read": (C.c_int, [_P, C.c_uint64, C.c_int, C.c_uint64, C.c_uint64, _P]),
+    "zoicb_gather_destroy": (None, [_P]),
     "zoicb_kernel_launches": (C.c_uint64, []),
     "zoicb_last_error": (C.c_char_p, []),
     "zoicb_version": (C.c_char_p, []),

@@ -29,7 +29,7 @@ constexpr int kTotalThreads = 288; // warp 0 adds, warps 1..8 load
 // lum = r*0.3 + g*0.59 + b*0.11 with the reference's association (src/zoic.cpp:234-262)
 __global__ void bokeh_lum_kernel(const float* __restrict__ rgb, int nch, size_t np, float* __restrict__ lum) {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < np; i += (size_t)gridDim.x * blockDim.x) {
-        const float* px = rgb + i * nch;
+        const float* px = rgb + i * nch;   // nch >= 3 here: the reference ignores images with fewer channels (:135-137)
         lum[i] = xadd(xadd(xmul(px[0], 0.3f), xmul(px[1], 0.59f)), xmul(px[2], 0.11f));
     }
 }
@@ -100,29 +100,15 @@ bokeh_pdf_rowmass_kernel(float* __restrict__ pdf, const float* __restrict__ tota
     if (r0 + lane < h) row_mass[r0 + lane] = acc;
 }
 
-// cutpoints of one CDF (camera_state.h): g[k] = first index whose value is greater than fl(k / n), k <= n, clamped to
-// the start of the flat tail; the tail start beyond
-__device__ void build_guide(const float* cdf, int n, uint16_t* g) {
-    int tail = n;   // start of the flat tail: the first entry that already carries the final value (n for a NaN table)
-    for (int i = 0; i < n; ++i) if (cdf[i] >= cdf[n - 1]) { tail = i; break; }
-    int pos = 0;
-    for (int k = 0; k < n + kBokehGuidePad; ++k) {
-        if (k > n) { g[k] = (uint16_t)tail; continue; }
-        const float t = xdiv((float)k, (float)n);
-        while (pos < n && !(t < cdf[pos])) ++pos;
-        g[k] = (uint16_t)(pos < tail ? pos : tail);
-    }
-}
-
 // rows by descending mass (:305-327), running row CDF (:330-341), row guide table
 __global__ void bokeh_rows_kernel(const float* __restrict__ row_mass, int h, int32_t* __restrict__ row_idx,
-                                  float* __restrict__ cdf_row, uint16_t* __restrict__ row_guide) {
+                                  float* __restrict__ cdf_row, int row_shift, uint16_t* __restrict__ row_guide) {
     if (blockIdx.x != 0 || threadIdx.x != 0) return;
     for (int r = 0; r < h; ++r) row_idx[r] = r;
     gnusort::sort(row_idx, (long)h, gnusort::Before<int32_t>{row_mass});
     float run = 0.0f;
     for (int r = 0; r < h; ++r) { run = xadd(run, row_mass[row_idx[r]]); cdf_row[r] = run; }
-    build_guide(cdf_row, h, row_guide);
+    build_guide_table(cdf_row, h, row_shift, row_guide);
 }
 
 // conditional pdf of a pixel within its row (:344-362), in place over pdf
@@ -139,7 +125,7 @@ __global__ void bokeh_cond_kernel(float* __restrict__ pdf, const float* __restri
 // row-relative index c against the row's own values makes the same comparisons and the same moves.
 __global__ void bokeh_columns_kernel(const float* __restrict__ cond, int w, int h, int32_t* __restrict__ scratch_idx,
                                      float* __restrict__ cdf_col, uint16_t* __restrict__ rel_col,
-                                     uint16_t* __restrict__ col_guide) {
+                                     int col_shift, uint16_t* __restrict__ col_guide) {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= h) return;
     const float* v = cond + (size_t)r * w;
@@ -155,24 +141,24 @@ __global__ void bokeh_columns_kernel(const float* __restrict__ cond, int w, int 
         cdf[c] = run;
         rel[c] = (uint16_t)k;
     }
-    build_guide(cdf, w, col_guide + (size_t)r * (w + kBokehGuidePad));
+    build_guide_table(cdf, w, col_shift, col_guide + (size_t)r * (((size_t)1 << col_shift) + 2));
 }
 
 }  // namespace
 
 cudaError_t launch_bokeh_build(const float* d_rgb, int w, int h, int nch, float* d_work, int32_t* d_scratch_idx,
                                float* d_total, float* d_row_mass, float* d_cdf_row, int32_t* d_row_idx,
-                               float* d_cdf_col, uint16_t* d_rel_col, uint16_t* d_row_guide, uint16_t* d_col_guide,
-                               cudaStream_t st, int* launches) {
+                               float* d_cdf_col, uint16_t* d_rel_col, int row_shift, int col_shift, uint16_t* d_row_guide,
+                               uint16_t* d_col_guide, cudaStream_t st, int* launches) {
     const size_t np = (size_t)w * h;
     if (np == 0) return cudaSuccess;
     const unsigned px_grid = (unsigned)((np + 255) / 256 < 148 * 8 ? (np + 255) / 256 : 148 * 8);
     bokeh_lum_kernel<<<px_grid, 256, 0, st>>>(d_rgb, nch, np, d_work);
     bokeh_total_kernel<<<1, kTotalThreads, 0, st>>>(d_work, np, d_total);
     bokeh_pdf_rowmass_kernel<<<(h + 31) / 32, 32, 0, st>>>(d_work, d_total, w, h, d_row_mass);
-    bokeh_rows_kernel<<<1, 32, 0, st>>>(d_row_mass, h, d_row_idx, d_cdf_row, d_row_guide);
+    bokeh_rows_kernel<<<1, 32, 0, st>>>(d_row_mass, h, d_row_idx, d_cdf_row, row_shift, d_row_guide);
     bokeh_cond_kernel<<<px_grid, 256, 0, st>>>(d_work, d_row_mass, w, np);
-    bokeh_columns_kernel<<<(h + 31) / 32, 32, 0, st>>>(d_work, w, h, d_scratch_idx, d_cdf_col, d_rel_col, d_col_guide);
+    bokeh_columns_kernel<<<(h + 31) / 32, 32, 0, st>>>(d_work, w, h, d_scratch_idx, d_cdf_col, d_rel_col, col_shift, d_col_guide);
     if (launches) *launches += 6;
     return cudaGetLastError();
 }

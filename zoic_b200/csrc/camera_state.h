@@ -11,7 +11,13 @@ namespace zoicb {
 constexpr int kMaxElements = 24;
 constexpr int kLutSize = 32;
 constexpr int kMaxBokehRows = 5120;  // row CDF + row indices are staged in 40 KB of shared memory
-constexpr int kBokehGuidePad = 4;   // guide tables hold n + 4 entries (k = 0 .. n + 3)
+// Guide ("cutpoint") tables of the inverse-CDF searches have G + 2 entries with G = 2^shift cells (see BokehTables).
+// Default resolution: the smallest power of two that is >= the table length, within [2^4, 2^16].
+inline int default_guide_shift(int n) {
+    int m = 4;
+    while (m < 16 && (1 << m) < n) ++m;
+    return m;
+}
 constexpr int kMaxTries = 25;  // reference src/zoic.cpp:1767
 
 // One refracting surface, rear element (nearest the sensor) first.  Everything the march needs per
@@ -75,19 +81,20 @@ struct BokehTables {
     const int32_t* row_indices;  // [h]
     const float* cdf_column;     // [h*w], rows in ORIGINAL row order (indexed by actual row * w)
     const uint16_t* rel_column;  // [h*w], columnIndices[c] - row*w
-    // guide ("cutpoint") tables of the two inverse-CDF searches: guide[k] = min(upper_bound(cdf, fl(k / G)), T) for
-    // k <= G, = T beyond (G = n = table length; kBokehGuidePad extra entries; T = start of the CDF's flat tail, the
-    // first entry that carries the final value), so that the answer for u < final lies in
-    // [guide[floor(u G) - 2], guide[floor(u G) + 3]] and the search only visits a handful of entries; u >= final => n
-    const uint16_t* row_guide;   // [h + kBokehGuidePad]
-    const uint16_t* col_guide;   // [h * (w + kBokehGuidePad)], by actual row like cdf_column
+    // Guide ("cutpoint") tables of the two inverse-CDF searches, with EXACT cells: G = 2^shift cells per table, and
+    // the cell of u is k = floor(u * G) -- exact in fp32 because G is a power of two, so no rounding margins are
+    // needed.  guide[k] = min(upper_bound(cdf, k / G), T) for k <= G and guide[G + 1] = T, where T is the start of
+    // the CDF's flat tail (the first entry that carries the final value; the zero-probability pixels around the
+    // aperture shape).  For 0 <= u < final the answer of std::upper_bound lies in [guide[k], guide[k + 1]] (k clamped
+    // to G), usually zero to two entries; u >= final => n.  The search result stays std::upper_bound's.
+    const uint16_t* row_guide;   // [2^row_shift + 2]
+    const uint16_t* col_guide;   // [h * (2^col_shift + 2)], by actual row like cdf_column
     // the lens coordinates of a pixel (src/zoic.cpp:441,466,479-484), tabulated with the reference's arithmetic:
     // dx_of_col[c] = fl(fl(fl(c - (h-1)/2) / fl(w)) * 2), dy_of_row[r] = fl(fl(-fl(r - (w-1)/2) / fl(h)) * 2)
     const float* dx_of_col;      // [w]
     const float* dy_of_row;      // [h]
     int32_t w, h;
-    int32_t valid;
-    int32_t pad;
+    int32_t row_shift, col_shift;   // log2 of the guide resolutions
 };
 
 struct CameraState {

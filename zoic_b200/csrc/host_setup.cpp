@@ -9,6 +9,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <fstream>
 #include <thread>
@@ -293,22 +294,12 @@ void build_lut(LensState* L, zoicb_constants* C, LutTraceFn fn, void* user) {
     Xor128 rng = {123456789u, 362436069u, 521288629u, 88675123u};
     for (uint32_t& d : draws) d = xor128_next(rng);
     std::vector<uint8_t> accept((size_t)n_film * per_film);
-    if (!fn || !fn(user, *L, film_x.data(), n_film, draws.data(), per_film, accept.data()))
-        lut_trace_host(*L, film_x.data(), n_film, draws.data(), per_film, accept.data());
-    const float ap = L->first_aperture;
+    std::vector<float> boxes((size_t)n_film * 4);
+    const int how = fn ? fn(user, *L, film_x.data(), n_film, draws.data(), per_film, accept.data(), boxes.data()) : 0;
+    if (how == 0) lut_trace_host(*L, film_x.data(), n_film, draws.data(), per_film, accept.data());
+    if (how != 2) lut_fold_boxes_host(draws.data(), accept.data(), n_film, per_film, L->first_aperture, boxes.data());
     for (int f = 0; f < n_film; ++f) {
-        float minx = 0, miny = 0, maxx = 0, maxy = 0;
-        for (int s = 0; s < per_film; ++s) {
-            size_t idx = (size_t)f * per_film + s;
-            if (!accept[idx]) continue;
-            float px = xmul(xsub(xmul(u32_to_unit(draws[2 * idx]), 2.0f), 1.0f), ap);
-            float py = xmul(xsub(xmul(u32_to_unit(draws[2 * idx + 1]), 2.0f), 1.0f), ap);
-            if (xadd(minx, miny) == 0.0f) { minx = maxx = px; miny = maxy = py; }  // :1423, re-arms on an exact 0 sum
-            if (px > maxx) maxx = px;
-            if (py > maxy) maxy = py;
-            if (px < minx) minx = px;
-            if (py < miny) miny = py;
-        }
+        const float minx = boxes[4 * f], miny = boxes[4 * f + 1], maxx = boxes[4 * f + 2], maxy = boxes[4 * f + 3];
         C->lutKey[f] = film_x[f];
         C->lutMinX[f] = minx; C->lutMinY[f] = miny; C->lutMaxX[f] = maxx; C->lutMaxY[f] = maxy;
         // boundingBox2d::getCentroid / getMaxScale (src/zoic.cpp:495-517)
@@ -386,8 +377,8 @@ struct ByValueDesc {
 };
 
 zoicb_status check_bokeh_image_impl(const float* rgb, int w, int h, int nch, std::string* err) {
-    if (!rgb || w <= 0 || h <= 0 || nch < 3 || (long long)w * h > (1ll << 26)) {
-        *err = "bokeh image needs pixels with at least 3 channels";
+    if (!rgb || w <= 0 || h <= 0 || nch < 1 || (long long)w * h > (1ll << 26)) {
+        *err = "useImage is set but there are no usable pixels";   // the reference: "Couldn't open bokeh image!" + abort (:1587-1591)
         return ZOICB_ERR_BOKEH_IMAGE;
     }
     if (w > 65535) { *err = "bokeh image wider than 65535 pixels"; return ZOICB_ERR_UNSUPPORTED; }
@@ -400,6 +391,7 @@ zoicb_status check_bokeh_image_impl(const float* rgb, int w, int h, int nch, std
 zoicb_status build_bokeh(const float* rgb, int w, int h, int nch, HostBokeh* out, std::string* err) {
     zoicb_status ok = check_bokeh_image_impl(rgb, w, h, nch, err);
     if (ok != ZOICB_OK) return ok;
+    const int row_shift = out->row_shift, col_shift = out->col_shift;
     const int np = w * h;
     std::vector<float> lum(np), pdf(np), row_mass(h), cond(np);
     float total = 0.0f;
@@ -442,26 +434,35 @@ zoicb_status build_bokeh(const float* rgb, int w, int h, int nch, HostBokeh* out
     }
     // guide tables for the device-side searches (camera_state.h): they only narrow the range the search visits,
     // the result stays std::upper_bound's
-    auto guide = [](const float* cdf, int n, uint16_t* g) {
-        // start of the flat tail: the first entry that already carries the final value (n when the table is NaN)
-        int tail = n;
-        for (int i = 0; i < n; ++i) if (cdf[i] >= cdf[n - 1]) { tail = i; break; }
-        int pos = 0;
-        for (int k = 0; k < n + kBokehGuidePad; ++k) {
-            if (k > n) { g[k] = (uint16_t)tail; continue; }
-            const float t = (float)k / (float)n;
-            while (pos < n && !(t < cdf[pos])) ++pos;   // first index whose value is greater than t; t grows with k
-            g[k] = (uint16_t)(pos < tail ? pos : tail);
-        }
-    };
-    out->row_guide.resize(h + kBokehGuidePad);
-    guide(out->cdf_row.data(), h, out->row_guide.data());
-    out->col_guide.resize((size_t)h * (w + kBokehGuidePad));
-    for (int r = 0; r < h; ++r) guide(out->cdf_column.data() + (size_t)r * w, w, out->col_guide.data() + (size_t)r * (w + kBokehGuidePad));
+    out->row_shift = row_shift > 0 ? row_shift : default_guide_shift(h);
+    out->col_shift = col_shift > 0 ? col_shift : default_guide_shift(w);
+    const size_t gr = ((size_t)1 << out->row_shift) + 2, gc = ((size_t)1 << out->col_shift) + 2;
+    out->row_guide.resize(gr);
+    build_guide_table(out->cdf_row.data(), h, out->row_shift, out->row_guide.data());
+    out->col_guide.resize((size_t)h * gc);
+    for (int r = 0; r < h; ++r) build_guide_table(out->cdf_column.data() + (size_t)r * w, w, out->col_shift, out->col_guide.data() + (size_t)r * gc);
     return ZOICB_OK;
 }
 
 }  // namespace
+
+void lut_fold_boxes_host(const uint32_t* draws, const uint8_t* accept, int n_film, int per_film, float ap, float* boxes) {
+    for (int f = 0; f < n_film; ++f) {
+        float minx = 0, miny = 0, maxx = 0, maxy = 0;
+        for (int s = 0; s < per_film; ++s) {
+            size_t idx = (size_t)f * per_film + s;
+            if (!accept[idx]) continue;
+            float px = xmul(xsub(xmul(u32_to_unit(draws[2 * idx]), 2.0f), 1.0f), ap);
+            float py = xmul(xsub(xmul(u32_to_unit(draws[2 * idx + 1]), 2.0f), 1.0f), ap);
+            if (xadd(minx, miny) == 0.0f) { minx = maxx = px; miny = maxy = py; }  // :1423, re-arms on an exact 0 sum
+            if (px > maxx) maxx = px;
+            if (py > maxy) maxy = py;
+            if (px < minx) minx = px;
+            if (py < miny) miny = py;
+        }
+        boxes[4 * f] = minx; boxes[4 * f + 1] = miny; boxes[4 * f + 2] = maxx; boxes[4 * f + 3] = maxy;
+    }
+}
 
 zoicb_status check_bokeh_image(const float* rgb, int w, int h, int nch, std::string* err) {
     return check_bokeh_image_impl(rgb, w, h, nch, err);
@@ -492,10 +493,23 @@ zoicb_status build_camera(const zoicb_params& p, const float* rgb, int w, int h,
     else if (p.exposureControl < 0.0f) S.weight_scale = xdiv(1.0f, xadd(1.0f, e2));
 
     if (p.useImage) {
-        zoicb_status rc;
-        if (bokeh_fn) {
-            rc = check_bokeh_image(rgb, w, h, nch, err);
-            if (rc == ZOICB_OK && !bokeh_fn(bokeh_user, rgb, w, h, nch, &out->bokeh)) {
+        zoicb_status rc = check_bokeh_image(rgb, w, h, nch, err);
+        if (rc != ZOICB_OK) return rc;
+        // guide resolutions (camera_state.h); ZOICB_GUIDE_ROW_LOG2 / ZOICB_GUIDE_COL_LOG2 override them for A/B runs
+        auto shift_from_env = [](const char* name, int n) {
+            const char* v = std::getenv(name);
+            const int m = v ? std::atoi(v) : 0;
+            return (m >= 1 && m <= 16) ? m : default_guide_shift(n);
+        };
+        out->bokeh.row_shift = shift_from_env("ZOICB_GUIDE_ROW_LOG2", h);
+        out->bokeh.col_shift = shift_from_env("ZOICB_GUIDE_COL_LOG2", w);
+        if (nch < 3) {
+            // imageData::isValid() is false for fewer than 3 channels (src/zoic.cpp:135-137): the reference builds no
+            // tables and every bokehSample answers (0, 0) (:420-425).  Kept: the device gets a 1 x 1 stand-in (capi.cu).
+            out->bokeh.w = w; out->bokeh.h = h; out->bokeh.degenerate = true;
+            C.bokehWidth = w; C.bokehHeight = h;
+        } else if (bokeh_fn) {
+            if (!bokeh_fn(bokeh_user, rgb, w, h, nch, &out->bokeh)) {
                 *err = "building the bokeh tables on the device failed";
                 rc = ZOICB_ERR_CUDA;
             }

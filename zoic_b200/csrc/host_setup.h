@@ -16,7 +16,13 @@ struct HostBokeh {
     std::vector<float> cdf_row, cdf_column;
     std::vector<int32_t> row_indices, column_indices;
     std::vector<uint16_t> row_guide, col_guide;   // search accelerators for the device (camera_state.h); not part of parity
-    bool valid() const { return w > 0 && h > 0; }
+    int row_shift = 0, col_shift = 0;             // log2 of the guide resolutions; set by build_camera before the tables are built
+    // The reference accepts an image with 1 or 2 channels but treats it as invalid (imageData::isValid wants >= 3,
+    // src/zoic.cpp:135-137): no tables, and every bokehSample returns the lens centre (0, 0) (:420-425).  `degenerate`
+    // marks such an image: w, h hold its size, the tables stay empty, and the device gets a 1 x 1 stand-in table whose
+    // only answer is (0, 0).
+    bool degenerate = false;
+    bool valid() const { return w > 0 && h > 0 && !degenerate; }
 };
 
 struct HostCamera {
@@ -28,17 +34,22 @@ struct HostCamera {
     std::vector<LensRow> rows;     // rear element first, after all rescaling
 };
 
-// A callback that classifies LUT candidate rays (accept = passes the whole stack).  The C-ABI passes a
-// GPU implementation; tests may pass nothing to use the host threads.
-typedef bool (*LutTraceFn)(void* user, const LensState& lens, const float* film_x, int n_film,
-                           const uint32_t* draws, int samples_per_film, uint8_t* accept);
+// A callback that classifies the exit-pupil LUT candidate rays (accept = passes the whole stack) and, if it can, also
+// folds the accepted candidates of every film position into the reference's bounding box (src/zoic.cpp:1421-1440).
+// Returns 0 on failure (the host threads take over), 1 when `accept` [n_film * per_film] is filled (the host replays the
+// boxes), 2 when `boxes` [n_film][4] = (min.x, min.y, max.x, max.y) is filled.  The C-ABI passes the GPU implementation.
+typedef int (*LutTraceFn)(void* user, const LensState& lens, const float* film_x, int n_film,
+                          const uint32_t* draws, int samples_per_film, uint8_t* accept, float* boxes);
+
+// the reference's in-order fold of one film position's accepted candidates, re-arm quirk (:1423) included
+void lut_fold_boxes_host(const uint32_t* draws, const uint8_t* accept, int n_film, int per_film, float ap, float* boxes);
 
 // A callback that builds the image-based aperture tables (all members of HostBokeh) from a validated image.
 // The C-ABI passes the GPU build (bokeh_build.cu); without one the host statement runs
 // (zoicb_setup_host_only, which has no device).
 typedef bool (*BokehBuildFn)(void* user, const float* rgb, int w, int h, int nch, HostBokeh* out);
 
-// What zoicb_create accepts as a bokeh image (>= 3 channels, <= 65535 columns, <= kMaxBokehRows rows).
+// What zoicb_create accepts as a bokeh image (>= 1 channel, <= 65535 columns, <= kMaxBokehRows rows).
 zoicb_status check_bokeh_image(const float* rgb, int w, int h, int nch, std::string* err);
 // idx = 0..n-1 ordered by the toolchain's std::sort with the reference's "greater by value" comparator shape
 void std_sort_desc(const float* values, int n, int32_t* idx);

@@ -8,7 +8,7 @@
 #include "lens_math.cuh"
 
 #ifndef ZOICB_BOKEH_COUNT
-#define ZOICB_BOKEH_COUNT 0   // 8: resolve brackets of up to 8 entries by counting (independent loads); 0: always halve
+#define ZOICB_BOKEH_COUNT 8   // brackets of up to this many entries (warp maximum) are resolved by counting; 0: always halve
 #endif
 #ifndef ZOICB_BOKEH_DXY_TABLES
 #define ZOICB_BOKEH_DXY_TABLES 1   // +2..3 % on config 3 (profiles/r01b_ab.txt); 0 = the divisions in the kernel
@@ -29,43 +29,42 @@ __device__ __forceinline__ void store_ray(RayRecord* __restrict__ rays, uint64_t
 // ------------------------------------------------------------------------------------------------
 // image-based aperture sampling (reference imageData::bokehSample, src/zoic.cpp:420-485)
 // ------------------------------------------------------------------------------------------------
-// std::upper_bound over a[0..n): first index whose value is greater than u.  The guide table (camera_state.h)
-// brackets the answer: with k = floor(u n) -- computed in fp32, so off by at most one -- the thresholds
-// fl((k-2)/n) <= u < fl((k+3)/n) hold with room for every rounding involved, hence
-//   guide[k-2] <= answer <= guide[k+3],
-// a handful of entries (a uniform u meets about four of them on average, whatever the image).  The guide entries are
-// clamped to the start of the CDF's flat tail (the zero-probability pixels around the aperture shape all carry the final
-// value): u >= final is answered directly (= n), anything smaller lies at or before the tail, so no bracket ever spans
-// it (without the clamp a quarter of all warps had one lane whose bracket was the whole tail).
-// Brackets of up to 8 entries -- all of them for the benchmark image -- are resolved by COUNTING the entries that are
-// not greater than u: eight independent loads instead of three dependent ones.  Longer brackets (warp-uniform
-// decision), NaN and negative u (whole range) take the libstdc++ first/len halving with a warp-uniform number of
-// rounds and predicated updates: no lane leaves the loop early.  (With a data-dependent trip count ptxas 12.9 let the
-// early lanes run ahead and re-use the uniform registers that hold the table pointers while the late lanes were
-// still reading them.)
+// std::upper_bound over a[0..n): first index whose value is greater than u.  The guide table (camera_state.h) has
+// G = 2^shift EXACT cells: k = floor(u G) is exact in fp32, so for 0 <= u < final the answer lies in
+//   [guide[k], guide[k + 1]]           (k clamped to G; guide[G + 1] = T, the start of the CDF's flat tail)
+// -- zero to two entries for an aperture-shaped image at G >= n -- and u >= final is answered directly (= n).  The guide
+// entries are clamped to T (the zero-probability pixels around the aperture shape all carry the final value), so no
+// bracket ever spans the flat tail.
+// Brackets of up to ZOICB_BOKEH_COUNT entries (warp maximum) are resolved by COUNTING the entries that are not greater
+// than u: independent, predicated loads (a lane only loads the entries of its own bracket) instead of a chain of
+// dependent probes.  Longer brackets (photograph-like images whose CDF is nearly flat towards 1), NaN and negative u
+// (whole range) take the libstdc++ first/len halving with a warp-uniform number of rounds and predicated updates: no
+// lane leaves the loop early.  (With a data-dependent trip count ptxas 12.9 let the early lanes run ahead and re-use the
+// uniform registers that hold the table pointers while the late lanes were still reading them.)
 template <typename Load, typename Guide>
-__device__ __forceinline__ int upper_bound_guided(int n, float u, Load load, Guide guide) {
+__device__ __forceinline__ int upper_bound_guided(int n, int shift, float u, Load load, Guide guide) {
     int first = 0, len = n;
     bool past = false;
     if (u >= 0.0f) {
-        const float f = u * (float)n;
-        const int k = f >= (float)n ? n : (int)f;
-        first = guide(k >= 2 ? k - 2 : 0);
-        len = guide(k + 3) - first;
-        past = u >= load(n - 1);   // false for a NaN table (black image): those guides are not clamped
+        const int G = 1 << shift;
+        const float f = u * (float)G;   // exact: G is a power of two
+        const int k = f >= (float)G ? G : (int)f;
+        first = guide(k);
+        len = guide(k + 1) - first;
+        past = u >= load(n - 1);   // false for a NaN table (black image): its guides all hold n
     }
+    const int maxlen = (int)__reduce_max_sync(__activemask(), (unsigned)len);
     constexpr int kCount = ZOICB_BOKEH_COUNT;
-    if (kCount > 0 && __all_sync(__activemask(), len <= kCount)) {
+    if (kCount > 0 && maxlen <= kCount) {
         int cnt = 0;
 #pragma unroll
         for (int j = 0; j < kCount; ++j) {
-            const int i = first + j;
-            const float v = load(i < n ? i : n - 1);
-            cnt += (j < len && !(u < v)) ? 1 : 0;
+            if (j >= maxlen) break;   // warp-uniform
+            if (j < len) cnt += (u < load(first + j)) ? 0 : 1;
         }
         return past ? n : first + cnt;
     }
-    const int rounds = 32 - __clz(__reduce_max_sync(__activemask(), (unsigned)len));
+    const int rounds = 32 - __clz(maxlen);
     for (int it = 0; it < rounds; ++it) {
         const int half = len >> 1;
         const int mid = first + half;
@@ -91,17 +90,18 @@ struct BokehView {
     const float* dx_of_col;
     const float* dy_of_row;
     int w, h;
+    int row_shift, col_shift;
 };
 
 __device__ __forceinline__ void bokeh_sample(const BokehView& b, float u_row, float u_col, float* dx, float* dy) {
-    int r = upper_bound_guided(b.h, u_row, [&](int i) { return s_rows[i]; }, [&](int k) { return (int)__ldg(b.row_guide + k); });
+    int r = upper_bound_guided(b.h, b.row_shift, u_row, [&](int i) { return s_rows[i]; }, [&](int k) { return (int)__ldg(b.row_guide + k); });
     if (r >= b.h) r = b.h - 1;
     const int row = __float_as_int(s_rows[b.h + r]);
     const int rrow = row - ((b.w - 1) / 2);  // centred with the WIDTH (:441)
     const int start = row * b.w;
     const float* __restrict__ col = b.cdf_col + start;
-    const uint16_t* __restrict__ cg = b.col_guide + row * (b.w + kBokehGuidePad);
-    int c = upper_bound_guided(b.w, u_col, [&](int i) { return __ldg(col + i); }, [&](int k) { return (int)__ldg(cg + k); });
+    const uint16_t* __restrict__ cg = b.col_guide + row * ((1 << b.col_shift) + 2);
+    int c = upper_bound_guided(b.w, b.col_shift, u_col, [&](int i) { return __ldg(col + i); }, [&](int k) { return (int)__ldg(cg + k); });
     if (c >= b.w) c = b.w - 1;
     const int rel = (int)__ldg(b.rel_col + start + c);
 #if ZOICB_BOKEH_DXY_TABLES
@@ -142,6 +142,7 @@ __device__ __forceinline__ BokehView stage_bokeh(const CameraState& cam) {
     b.col_guide = cam.bokeh.col_guide;
     b.dx_of_col = cam.bokeh.dx_of_col;
     b.dy_of_row = cam.bokeh.dy_of_row;
+    b.row_shift = cam.bokeh.row_shift; b.col_shift = cam.bokeh.col_shift;
     for (int i = threadIdx.x; i < b.h; i += blockDim.x) {
         s_rows[i] = cam.bokeh.cdf_row[i];
         s_rows[b.h + i] = __int_as_float(cam.bokeh.row_indices[i]);
@@ -297,21 +298,20 @@ __device__ __forceinline__ void lens_sample_fast(const BokehView& b, float u, fl
 // ------------------------------------------------------------------------------------------------
 // launch helpers
 // ------------------------------------------------------------------------------------------------
-inline int sm_count() {
-    static int count = 0;
-    if (!count) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&count, cudaDevAttrMultiProcessorCount, dev);
-        if (count <= 0) count = 148;
+inline int sm_count() {   // of the calling thread's current device (cached per device)
+    static int counts[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) dev = 0;
+    int c = counts[dev];
+    if (!c) {
+        cudaDeviceGetAttribute(&c, cudaDevAttrMultiProcessorCount, dev);
+        if (c <= 0) c = 148;
+        counts[dev] = c;
     }
-    return count;
+    return c;
 }
 
-// kolb_pool.cu
-cudaError_t launch_kolb_pool(const CameraState& cam, const float4* samples, uint64_t n, uint64_t first_index, uint64_t seed,
-                             RayRecord* rays, DeviceStats* stats, cudaStream_t st, const Workspace& ws, size_t rows_smem,
-                             int* launches);
 // kolb_pool2.cu (two rays per lane, packed fp32)
 cudaError_t launch_kolb_pool2(const CameraState& cam, const float4* samples, uint64_t n, uint64_t first_index, uint64_t seed,
                               RayRecord* rays, DeviceStats* stats, cudaStream_t st, const Workspace& ws, size_t rows_smem,

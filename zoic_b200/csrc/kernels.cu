@@ -3,9 +3,9 @@
 // Behavioural reference: camera_create_ray, reference src/zoic.cpp:1752-1990 (thin-lens branch
 // :1771-1848, raytraced branch :1850-1964, tail :1974-1987) and its callees.
 //
-// Data layout in HBM: samples float4 (sx, sy, lensx, lensy); outputs two float4
-// arrays (origin.xyz, weight) and (dir.xyz, tries), index = sample index, so a warp reads 512 B and
-// writes 2 x 512 B contiguous.  Camera constants travel as a __grid_constant__ kernel parameter.
+// Data layout in HBM: samples float4 (sx, sy, lensx, lensy); outputs ONE 32-byte record
+// per sample (origin.xyz, weight, dir.xyz, tries; index = sample index), written with a single 256-bit store.
+// Camera constants travel as a __grid_constant__ kernel parameter.
 #include <cuda_runtime.h>
 #include <math_constants.h>
 #include <stdlib.h>
@@ -268,6 +268,76 @@ lut_trace_kernel(const __grid_constant__ LensState L, const float* __restrict__ 
 }
 
 // ------------------------------------------------------------------------------------------------
+// exit-pupil LUT bounding boxes (src/zoic.cpp:1421-1440).  The reference folds the accepted
+// candidates of a film position into its bounding box IN ORDER, and the fold is not a plain min/max: whenever the
+// running min.x + min.y is exactly 0 -- always for the first accepted candidate (the box starts at the origin),
+// and again later if the two minima happen to cancel -- the box is RE-ARMED to the current point (:1423).  One warp
+// per film position walks its candidates 32 at a time: warp prefix minima / maxima by shuffles give every lane the
+// box BEFORE its candidate; if no accepted lane sees the re-arm condition the chunk is an ordinary min/max (and a
+// re-arm inside the chunk would have been seen by its own lane, whose prefix is still exact), otherwise lane 0 replays
+// the 32 candidates with the reference's statement.  box = (min.x, min.y, max.x, max.y) per film position.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32)
+lut_bbox_kernel(const uint32_t* __restrict__ draws, const uint8_t* __restrict__ accept, int per_film, float ap,
+                float4* __restrict__ boxes) {
+    const int f = blockIdx.x;
+    const unsigned lane = threadIdx.x;
+    const uint2* d = reinterpret_cast<const uint2*>(draws) + (size_t)f * per_film;
+    const uint8_t* acc = accept + (size_t)f * per_film;
+    float minx = 0.0f, miny = 0.0f, maxx = 0.0f, maxy = 0.0f;   // warp-uniform running box
+    const float inf = __int_as_float(0x7f800000);
+    for (int base = 0; base < per_film; base += 32) {
+        const int s = base + (int)lane;
+        bool a = false;
+        float px = 0.0f, py = 0.0f;
+        if (s < per_film) {
+            a = acc[s] != 0;
+            const uint2 k = d[s];
+            px = xmul(xsub(xmul(u32_to_unit(k.x), 2.0f), 1.0f), ap);
+            py = xmul(xsub(xmul(u32_to_unit(k.y), 2.0f), 1.0f), ap);
+        }
+        if (!__any_sync(0xffffffffu, a)) continue;
+        // inclusive prefix min / max over the accepted candidates of the chunk (identity for the others)
+        float lminx = a ? px : inf, lminy = a ? py : inf, lmaxx = a ? px : -inf, lmaxy = a ? py : -inf;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const float ax = __shfl_up_sync(0xffffffffu, lminx, o), ay = __shfl_up_sync(0xffffffffu, lminy, o);
+            const float bx = __shfl_up_sync(0xffffffffu, lmaxx, o), by = __shfl_up_sync(0xffffffffu, lmaxy, o);
+            // (earlier, later) -> the later value replaces the earlier one only when strictly smaller / larger, as in the
+            // reference's sequential `if (p < min) min = p`
+            if (lane >= (unsigned)o) {
+                lminx = lminx < ax ? lminx : ax; lminy = lminy < ay ? lminy : ay;
+                lmaxx = lmaxx > bx ? lmaxx : bx; lmaxy = lmaxy > by ? lmaxy : by;
+            }
+        }
+        // the box before this lane's candidate: running box folded with the candidates of the lower lanes
+        float ex = __shfl_up_sync(0xffffffffu, lminx, 1), ey = __shfl_up_sync(0xffffffffu, lminy, 1);
+        if (lane == 0) { ex = inf; ey = inf; }
+        const float before_minx = ex < minx ? ex : minx, before_miny = ey < miny ? ey : miny;
+        const bool rearm = a && xadd(before_minx, before_miny) == 0.0f;
+        if (__any_sync(0xffffffffu, rearm)) {
+            // rare: replay the chunk in order with the reference's statement
+            for (int j = 0; j < 32; ++j) {
+                const bool aj = __shfl_sync(0xffffffffu, a ? 1 : 0, j) != 0;
+                const float qx = __shfl_sync(0xffffffffu, px, j), qy = __shfl_sync(0xffffffffu, py, j);
+                if (!aj) continue;
+                if (xadd(minx, miny) == 0.0f) { minx = maxx = qx; miny = maxy = qy; }
+                if (qx > maxx) maxx = qx;
+                if (qy > maxy) maxy = qy;
+                if (qx < minx) minx = qx;
+                if (qy < miny) miny = qy;
+            }
+        } else {
+            const float cx = __shfl_sync(0xffffffffu, lminx, 31), cy = __shfl_sync(0xffffffffu, lminy, 31);
+            const float dx = __shfl_sync(0xffffffffu, lmaxx, 31), dy = __shfl_sync(0xffffffffu, lmaxy, 31);
+            minx = cx < minx ? cx : minx; miny = cy < miny ? cy : miny;
+            maxx = dx > maxx ? dx : maxx; maxy = dy > maxy ? dy : maxy;
+        }
+    }
+    if (lane == 0) boxes[f] = make_float4(minx, miny, maxx, maxy);
+}
+
+// ------------------------------------------------------------------------------------------------
 // draw.zoic ray paths: what the reference's -D_DRAW build writes from inside
 // traceThroughLensElements (src/zoic.cpp:1121-1128, :1146-1153) for a drawn sample -- per surface whose rim test
 // passed, the ray origin and the hit point (z, y); after the last surface, the hit point and the exit direction --
@@ -385,19 +455,17 @@ static cudaError_t launch_variant(const CameraState& cam, int mode, const float4
     if (mode == 1 && kModel == 1) {  // guarded fast path + exact re-run of the undecided samples
         cudaError_t e = cudaMemsetAsync(ws.counters, 0, 4 * sizeof(unsigned long long), st);
         if (e != cudaSuccess) return e;
-        // Three flavours of the pool kernel, chosen from the camera's calibration (host_setup.cpp: choose_split):
-        //   packed (two rays per lane, FFMA2)      -- most attempts survive the first surfaces (e.g. the double Gauss);
-        //   packed with a rim pre-test loop        -- most attempts die on the first surfaces (narrow-field lenses on a
-        //                                             wide sensor: 15-22 attempts per ray; the fisheye);
-        //   scalar with in-pass re-sampling        -- the previous kernel for those cameras, kept for A/B runs.
-        // ZOICB_POOL=1 / 2 / 3 forces scalar / packed / packed + pre-test (profiles/r01_ab_pool2.txt).
+        // Flavours of the pool kernel (kolb_pool2.cu: two rays per lane, FFMA2), chosen from the camera's calibration
+        // (host_setup.cpp: choose_split):
+        //   plain               -- most attempts survive the first surfaces (e.g. the double Gauss);
+        //   rim pre-test loop   -- most attempts die on the first surfaces (narrow-field lenses on a wide sensor:
+        //                          15-22 attempts per ray; the fisheye).
+        // ZOICB_POOL=2 / 3 forces plain / pre-test (A/B runs and the parity tests of both flavours on every lens).
         static const int force_pool = [] { const char* v = getenv("ZOICB_POOL"); return v ? atoi(v) : 0; }();
         CameraState c2 = cam;
         if (force_pool == 3) c2.lens.pretest = 1;
-        if (force_pool == 1 || force_pool == 2) c2.lens.pretest = 0;
-        const bool scalar_pool = force_pool == 1 || (force_pool == 0 && c2.lens.inner_retry != 0 && c2.lens.pretest == 0);
-        e = scalar_pool ? launch_kolb_pool(c2, samples, n, first_index, seed, rays, stats, st, ws, smem, launches)
-                        : launch_kolb_pool2(c2, samples, n, first_index, seed, rays, stats, st, ws, smem, launches);
+        if (force_pool == 2) c2.lens.pretest = 0;
+        e = launch_kolb_pool2(c2, samples, n, first_index, seed, rays, stats, st, ws, smem, launches);
         if (e != cudaSuccess) return e;
         kolb_exact_persistent_kernel<kImage, kLut, true><<<(unsigned)sm_count() * 3, threads, smem, st>>>(
             cam, samples, 0, first_index, seed, rays, stats, ws.counters + 2, ws.queue, ws.counters + 1,
@@ -501,6 +569,14 @@ cudaError_t launch_transform(const float* m3x4, const RayRecord* in, uint64_t n,
 cudaError_t launch_lut_trace(const LensState& L, const float* d_film_x, int n_film, int per_film, const uint32_t* d_draws,
                              uint8_t* d_accept, cudaStream_t st, int* launches) {
     lut_trace_kernel<<<grid_for((uint64_t)n_film * per_film, 256, 8), 256, 0, st>>>(L, d_film_x, n_film, per_film, d_draws, d_accept);
+    if (launches) *launches += 1;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_lut_bbox(const uint32_t* d_draws, const uint8_t* d_accept, int n_film, int per_film, float ap,
+                            float4* d_boxes, cudaStream_t st, int* launches) {
+    if (n_film <= 0) return cudaSuccess;
+    lut_bbox_kernel<<<n_film, 32, 0, st>>>(d_draws, d_accept, per_film, ap, d_boxes);
     if (launches) *launches += 1;
     return cudaGetLastError();
 }

@@ -25,16 +25,21 @@ cudaError_t launch_synth(uint32_t W, uint32_t H, uint32_t spp, uint64_t seed, ui
                          float4* out, cudaStream_t st, int* launches);
 cudaError_t launch_lut_trace(const LensState& L, const float* d_film_x, int n_film, int per_film, const uint32_t* d_draws,
                              uint8_t* d_accept, cudaStream_t st, int* launches);
+// bounding boxes of the accepted LUT candidates, folded in order with the reference's re-arm quirk (:1423):
+// d_boxes[f] = (min.x, min.y, max.x, max.y)
+cudaError_t launch_lut_bbox(const uint32_t* d_draws, const uint8_t* d_accept, int n_film, int per_film, float ap,
+                            float4* d_boxes, cudaStream_t st, int* launches);
 cudaError_t launch_draw_paths(const CameraState& cam, const float4* samples, uint32_t n, const unsigned long long* indices,
                               uint64_t first_index, uint64_t seed,
                               float4* quads, uint8_t* kinds, uint32_t* counts, uint32_t cap, cudaStream_t st, int* launches);
 cudaError_t launch_transform(const float* m3x4, const RayRecord* in, uint64_t n, RayRecord* out, cudaStream_t st, int* launches);
 // Image-based aperture tables built on the device (bokeh_build.cu).  d_work [w*h] floats and d_scratch_idx [w*h]
-// int32 are scratch; d_total [2]; d_row_mass [h]; the remaining pointers are the tables of BokehTables.
+// int32 are scratch; d_total [2]; d_row_mass [h]; the remaining pointers are the tables of BokehTables (guide tables:
+// 2^row_shift + 2 and h * (2^col_shift + 2) entries).
 cudaError_t launch_bokeh_build(const float* d_rgb, int w, int h, int nch, float* d_work, int32_t* d_scratch_idx,
                                float* d_total, float* d_row_mass, float* d_cdf_row, int32_t* d_row_idx,
-                               float* d_cdf_col, uint16_t* d_rel_col, uint16_t* d_row_guide, uint16_t* d_col_guide,
-                               cudaStream_t st, int* launches);
+                               float* d_cdf_col, uint16_t* d_rel_col, int row_shift, int col_shift, uint16_t* d_row_guide,
+                               uint16_t* d_col_guide, cudaStream_t st, int* launches);
 cudaError_t measure_fp32_peak(double* tflops, int* launches);
 
 }  // namespace zoicb

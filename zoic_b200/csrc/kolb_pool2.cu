@@ -1,6 +1,7 @@
 // kolb_pool2.cu -- the GUARDED kernel of the raytraced lens, packed-fp32 edition.
 //
-// Same schedule as kolb_pool.cu (per-warp slot pool in shared memory, two-stage march, ballot/popc stacks), but
+// Schedule: per-warp slot pool in shared memory, two-stage march, ballot/popc stacks (the scalar one-ray-per-lane
+// kernel of the same design was retired in round 2; its A/B numbers are in profiles/r01_ab_pool2.txt).  Here
 // every lane carries TWO rays through each pass and all fp32 arithmetic is issued as sm_100 packed instructions
 // (fma/add/mul.rn.f32x2 -> SASS FFMA2/FADD2/FMUL2): one issue slot does the work for both rays, which frees
 // issue slots for the MUFU / compare / select / integer instructions the march also needs (the scalar kernel is

@@ -1,8 +1,10 @@
 """Sharding of a sample range over ranks and the final gather of the ray buffer.
 
 Every sample is independent (per-sample retry streams), so ranks take contiguous index ranges and there is no
-data-path collective; the only collective is the optional gather of the finished ray buffers and a sum of the
-counters.  torch.distributed is the plumbing: NCCL over NVLink on GPUs, gloo in the CPU tests.
+data-path collective; the only exchange is the final gather of the finished ray tiles to the consumer rank, which is
+libzoicb's own (zoic_b200.Gather / csrc/gather.cu: generate kernels storing into the consumer's memory over NVLink, a
+copy-engine push, or ncclSend/ncclRecv).  torch.distributed is plumbing here: it carries the set-up handshake
+(connect_gather), the counters (reduce_stats) and, in the CPU tests, a gloo all-gather standing in for NVLink.
 """
 
 
@@ -47,39 +49,28 @@ def reduce_stats(stats, device, group=None):
     return {k: int(v) for k, v in zip(keys, t.tolist())}
 
 
-class TileGather:
-    """Double-buffered all-gather of finished ray tiles: the gather of tile k runs on the collective's
-    own stream / thread while tile k+1 is generated into the other tile buffer.  All ranks submit tiles of the same
-    shape.  Usage, with two tile buffers t[0], t[1]:
+def job_share(n, passes, rank, world):
+    """Rank `rank`'s share of an n-sample frame laid out in `passes` passes (zoic_b200.workloads): whole passes, i.e. the
+    contiguous index range [rank n / world, (rank + 1) n / world).  Every rank renders every pixel of the film with its
+    own samples, so all ranks carry the same mix of vignetted and clear pixels (bands of pixel rows lost 11 % to
+    imbalance, profiles/r01c_bench_headline_8gpu_bands.json), and the rays of the job do not depend on `world`."""
+    if passes % world or n % passes:
+        raise ValueError("world size %d does not divide the frame's %d passes" % (world, passes))
+    per = (n // passes) * (passes // world)
+    return rank * per, per
 
-        g = TileGather(rows, width, dtype, device)
-        for k in range(tiles):
-            b = k & 1
-            g.wait(b)                    # the gather that last read t[b] has finished: t[b] may be overwritten
-            generate(out=t[b])
-            g.submit(b, t[b])            # asynchronous; g.wait(b) later returns the gathered [world * rows, width] tile
-        g.drain()
-    """
 
-    def __init__(self, rows, width, dtype, device, group=None):
-        import torch
-        import torch.distributed as dist
-        self.group = group
-        self.world = dist.get_world_size(group)
-        self.full = [torch.empty((self.world * rows, width), dtype=dtype, device=device) for _ in range(2)]
-        self.work = [None, None]
-
-    def submit(self, b, tile):
-        import torch.distributed as dist
-        assert self.work[b] is None, "wait(b) before re-using buffer b"
-        self.work[b] = dist.all_gather_into_tensor(self.full[b], tile.contiguous(), group=self.group, async_op=True)
-
-    def wait(self, b):
-        """Blocks (stream-orders, on CUDA) until the gather submitted for buffer b is complete; returns the gathered tile."""
-        if self.work[b] is not None:
-            self.work[b].wait()
-            self.work[b] = None
-        return self.full[b]
-
-    def drain(self):
-        return [self.wait(0), self.wait(1)]
+def connect_gather(gather, group=None):
+    """Collective set-up of a zoic_b200.Gather: exchanges the ranks' IPC blobs (and, for the NCCL transport, a unique id
+    made on rank 0) over torch.distributed -- plumbing only; the data path is libzoicb's."""
+    import torch.distributed as dist
+    from .camera import nccl_unique_id
+    world = dist.get_world_size(group)
+    blobs = [None] * world
+    dist.all_gather_object(blobs, gather.export(), group=group)
+    gather.connect(blobs)
+    if gather.transport == "nccl":
+        ident = [nccl_unique_id() if dist.get_rank(group) == 0 else None]
+        dist.broadcast_object_list(ident, src=0, group=group)
+        gather.init_nccl(ident[0])
+    dist.barrier(group=group)
