@@ -1,15 +1,20 @@
 #!/usr/bin/env python
 """bench.py -- camera Mrays/s on the configurations of BASELINE.json.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload headline|config1..4] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload headline|config1..4|config5:<lens>] [--impl ours|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
         bench.py --gpus N --steps K --warmup W
 
-A "step" is one pass of the hot path (zoicb_generate, i.e. camera_create_ray for a whole batch) over one
-batch of synthetic samples that is already resident in HBM.  The default workload is the headline metric of
-BASELINE.json: the Kolb double-Gauss f/2.0 camera on a 3840x2160x256spp sample grid (2.12 G rays per GPU per
-step; rank r takes pass r -- its own 256 samples of every pixel -- of a 256*N spp job: weak scaling, no data-path
-collective).  Rank 0 prints ONE JSON line; see DESIGN.md section 7 for every key.
+A "step" is one pass of the hot path (camera_create_ray for every sample of the job) over one batch of synthetic
+samples.  The default workload is the headline metric of BASELINE.json: the Kolb double-Gauss f/2.0 camera on a
+3840x2160x256spp frame (2.12 G rays), laid out in 8 passes of 32 spp (zoic_b200/workloads.py) and STRONG-split over the
+GPUs: rank r of G generates passes [r 8/G, (r+1) 8/G) = samples [r N/G, (r+1) N/G) of the one fixed job.
+  * a share that fits in HBM is resident (16 B/sample in, 32 B/ray out) and a step is ONE zoicb_generate over it;
+  * a share that does not (config 4: 204 GB, config 5: 1.6 TB per lens) is STREAMED by zoicb_run_job: tiles of 2^27
+    samples synthesised on the device, generated, consumed by a checksum kernel, through rotating buffers.
+At N > 1 the line also carries `gather`: the same job with the final gather of every ray to rank 0 over NVLink
+(libzoicb's gather-to-consumer: kernels storing into rank 0's memory / copy-engine push / ncclSend-Recv), sequential and
+pipelined.  Rank 0 prints ONE JSON line; see DESIGN.md section 7 for every key.
 """
 import argparse
 import json
@@ -107,71 +112,97 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------------
-# CPU reference arm
+# CPU reference arm: the compiled unmodified reference (oracle/_ref), or the restatement where it is absent
 # ------------------------------------------------------------------------------------------------------
-def _cpu_worker(args):
-    """One process: build the camera with the compiled reference (or the port), time generate() on its share."""
-    kind, params, use_hex, W, H, spp, seed, first, n = args
-    import numpy as np
+_W = {}   # per worker process: camera + its slice of samples, built once
+
+
+def _cpu_init(kind, params, use_hex, synth, seed):
     from oracle import port
     from zoic_b200.synth import hex_bokeh_image
     image = hex_bokeh_image(255) if use_hex else None
-    s = port.synth_samples(W, H, spp, seed, first, n)
     if kind == "reference":
         from oracle import ref
-        cam = ref.RefCamera(image=image, **params)
+        _W["cam"] = ref.RefCamera(image=image, **params)
     else:
-        cam = port.PortCamera(image=image, **params)
+        _W["cam"] = port.PortCamera(image=image, **params)
+    _W["port"], _W["synth"], _W["seed"], _W["slices"] = port, synth, seed, {}
+
+
+def _cpu_run(job):
+    """One worker: generate() over its contiguous slice (synthesised once per slice and kept)."""
+    first, n, threads = job
+    key = (first, n)
+    if key not in _W["slices"]:
+        W, H, spp = _W["synth"]
+        _W["slices"][key] = _W["port"].synth_samples(W, H, spp, _W["seed"], first, n)
+    s = _W["slices"][key]
     t = time.perf_counter()
-    o, d, st = cam.generate(s, seed=seed, first_index=first)
-    dt = time.perf_counter() - t
-    cam.close()
-    return n, dt, float(np.asarray(o[:, 3]).sum())
+    if threads:
+        o, d, st = _W["cam"].generate(s, seed=_W["seed"], first_index=first, nthreads=threads)
+    else:
+        o, d, st = _W["cam"].generate(s, seed=_W["seed"], first_index=first)
+    return n, time.perf_counter() - t
 
 
-def cpu_reference_rate(wl, total_samples, cores=None):
-    """Mrays/s of the reference CPU camera_create_ray on `cores` host cores, one process per core (the
-    reference shares unsynchronised counters and a global RNG between threads), on a stratified sample of the
-    workload: `total_samples` samples split into one contiguous slice per process, spread evenly over the
-    sample grid."""
-    import multiprocessing as mp
-    from oracle import ref
-    kind = "reference" if ref.available() else "port"
-    cores = cores or os.cpu_count() or 1
-    per = max(1024, total_samples // cores)
-    stride = max(per, wl.n // cores)
-    jobs = [(kind, wl.params, wl.image() is not None, wl.W, wl.H, wl.spp, wl.seed, min(k * stride, max(0, wl.n - per)), per)
-            for k in range(cores)]
-    ctx = mp.get_context("spawn")
-    t0 = time.perf_counter()
-    with ctx.Pool(cores) as pool:
-        res = pool.map(_cpu_worker, jobs)
-    wall = time.perf_counter() - t0
-    n = sum(r[0] for r in res)
-    slowest = max(r[1] for r in res)
-    return {"value": n / slowest / 1e6, "unit": UNIT, "cores": cores, "kind": kind,
-            "sample": "%d samples: %d contiguous slices of %d spread evenly over the %s grid; rate = samples / slowest "
-                      "process (setup excluded)" % (n, cores, per, "%dx%dx%d" % (wl.W, wl.H, wl.spp)),
-            "seconds": slowest, "wall_seconds": wall}
+class CpuReference:
+    """The reference's CPU camera_create_ray on `cores` host cores: one PROCESS per core, each with its own camera node
+    (the reference shares unsynchronised counters and one global RNG between the threads of a node), each on one
+    contiguous slice of the workload, the slices spread evenly over the frame.  Workers and cameras persist across steps,
+    so a step times generate() only."""
+
+    def __init__(self, wl, cores=None):
+        import multiprocessing as mp
+        from oracle import ref
+        self.wl = wl
+        self.kind = "reference" if ref.available() else "port"
+        self.cores = cores or os.cpu_count() or 1
+        ctx = mp.get_context("spawn")
+        self.pool = ctx.Pool(self.cores, initializer=_cpu_init,
+                             initargs=(self.kind, wl.params, wl.image() is not None, (wl.W, wl.H, wl.spp_per_pass), wl.seed))
+
+    def rate(self, total_samples, threads=0):
+        wl, cores = self.wl, (1 if threads else self.cores)
+        per = max(1024, total_samples // cores)
+        stride = max(per, wl.n // cores)
+        jobs = [(min(k * stride, max(0, wl.n - per)), per, threads) for k in range(cores)]
+        t0 = time.perf_counter()
+        res = self.pool.map(_cpu_run, jobs, chunksize=1)
+        wall = time.perf_counter() - t0
+        n = sum(r[0] for r in res)
+        slowest = max(r[1] for r in res)
+        what = ("%d samples: %d contiguous slices of %d spread evenly over the %dx%dx%d frame; rate = samples / slowest "
+                "process (setup and sample synthesis excluded)" % (n, cores, per, wl.W, wl.H, wl.spp))
+        if threads:
+            what = ("%d samples, ONE camera node shared by %d threads as shipped (unsynchronised shared counters, "
+                    "src/zoic.cpp:533-534)" % (n, threads))
+        return {"value": n / slowest / 1e6, "unit": UNIT, "cores": threads or cores, "kind": self.kind, "sample": what,
+                "seconds": slowest, "wall_seconds": wall}
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
 
 
 def run_reference_arm(args, wl):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    cpu = CpuReference(wl)
     per_step = args.cpu_samples
+    for _ in range(min(args.warmup, 1)):
+        cpu.rate(per_step)   # also synthesises the slices
     vals, last = [], None
-    for _ in range(args.warmup if args.warmup < 2 else 1):
-        cpu_reference_rate(wl, max(per_step // 8, 8192))
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        last = cpu_reference_rate(wl, per_step)
+        last = cpu.rate(per_step)
         vals.append(last["value"])
     wall = time.perf_counter() - t0
+    cpu.close()
     value = sum(vals) / len(vals)
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": wl.describe(),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": last["cores"], "kind": last["kind"],
                              "sample": last["sample"]},
@@ -183,6 +214,39 @@ def run_reference_arm(args, wl):
 # ------------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------------
+def pcie_yardstick(torch, dev, barrier, reduce_max, mb=256, reps=6):
+    """Raw pinned-memory copy bandwidth of this rank with ALL ranks copying at the same time: H2D alone, D2H alone and
+    both directions together (GB/s; the slowest rank's figure).  The yardstick the e2e number is read against."""
+    n = mb << 20
+    h_up = torch.empty(n, dtype=torch.uint8).pin_memory()
+    h_dn = torch.empty(n, dtype=torch.uint8).pin_memory()
+    d_up = torch.empty(n, dtype=torch.uint8, device=dev)
+    d_dn = torch.empty(n, dtype=torch.uint8, device=dev)
+    s_up, s_dn = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+
+    def timed(up, down):
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            if up:
+                with torch.cuda.stream(s_up):
+                    d_up.copy_(h_up, non_blocking=True)
+            if down:
+                with torch.cuda.stream(s_dn):
+                    h_dn.copy_(d_dn, non_blocking=True)
+        s_up.synchronize()
+        s_dn.synchronize()
+        dt = reduce_max(time.perf_counter() - t0)
+        return reps * n / dt / 1e9
+
+    timed(True, True)   # warm-up
+    out = {"h2d_alone": timed(True, False), "d2h_alone": timed(False, True)}
+    both = timed(True, True)
+    out["h2d_d2h_concurrent_each"] = both
+    out["what"] = "%d MiB pinned copies, %d repetitions, all ranks at once, slowest rank; GB/s per direction" % (mb, reps)
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -192,10 +256,15 @@ def main():
     ap.add_argument("--workload", default="headline")
     ap.add_argument("--mode", default="default", choices=["default", "exact", "guarded"])
     ap.add_argument("--samples", type=int, default=0, help="override samples per GPU per step (debug)")
-    ap.add_argument("--spp", type=int, default=0, help="override samples per pixel (profiling: a small batch that still covers the whole film)")
+    ap.add_argument("--spp", type=int, default=0, help="override samples per pixel (profiling: a small job that still covers the whole film)")
+    ap.add_argument("--stream", action="store_true", help="stream the job through zoicb_run_job even if it would fit in HBM")
+    ap.add_argument("--tile-log2", type=int, default=27, help="streamed jobs: samples per tile")
     ap.add_argument("--e2e-samples", type=int, default=1 << 27)
-    ap.add_argument("--cpu-samples", type=int, default=1 << 22, help="CPU baseline sample size (all cores)")
-    ap.add_argument("--gather", action="store_true", help="N > 1: also time generation + NCCL all-gather of a 2^26-ray tile")
+    ap.add_argument("--cpu-samples", type=int, default=1 << 25, help="CPU baseline sample size (all cores)")
+    ap.add_argument("--census-rays", type=int, default=2_123_366_400, help="N = 1: rays of the GUARDED-vs-EXACT census (0 = off)")
+    ap.add_argument("--transports", default="fused,push,nccl", help="N > 1: gather transports to time")
+    ap.add_argument("--gather-tile-log2", type=int, default=24, help="N > 1: records per rank and round of the gather")
+    ap.add_argument("--no-gather", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -205,6 +274,7 @@ def main():
     wl = workloads.BY_NAME[args.workload]()
     if args.spp:
         wl.spp = args.spp
+        wl.passes = wl.passes if args.spp % wl.passes == 0 else 1
         wl.name += " [spp overridden: %d]" % args.spp
     if args.impl == "reference":
         run_reference_arm(args, wl)
@@ -212,7 +282,8 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from zoic_b200 import ZoicCamera, MODE_EXACT, MODE_GUARDED, camera as zcam
+    from zoic_b200 import ZoicCamera, Gather, MODE_EXACT, MODE_GUARDED, camera as zcam
+    from zoic_b200.distributed import connect_gather, job_share, shard_range
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -224,69 +295,95 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
 
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def reduce_max(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     cam = ZoicCamera(image=wl.image(), device=local, **wl.params)
+    create_times = cam.create_times()
     if args.mode == "exact":
         cam.set_mode(MODE_EXACT)
     elif args.mode == "guarded":
         cam.set_mode(MODE_GUARDED)
     mode_name = {MODE_EXACT: "exact", MODE_GUARDED: "guarded"}[cam.mode]
 
-    n = args.samples or wl.n
-    # memory: 16 B in + 32 B out per sample resident; shrink the per-step batch if the device cannot hold it
+    # Strong split of the ONE job: whole passes per rank (every rank renders the whole film: balanced vignetting; the
+    # job's rays are the same bits for every world size).  A frame whose passes the world does not divide falls back to a
+    # plain contiguous split.
+    try:
+        first, n = job_share(wl.n, wl.passes, rank, world)
+        split = "passes"
+    except ValueError:
+        first, n = shard_range(wl.n, rank, world)
+        split = "contiguous"
+    if args.samples:
+        n = min(n, args.samples)
+    counts = [n] * world
+    W, H, spp_pp, sseed = wl.synth_args()
     free, _total = torch.cuda.mem_get_info(dev)
-    while n * 48 > free * 0.9:
-        n //= 2
-    # Weak scaling: rank r owns samples [r*n, (r+1)*n) of a W x H x spp x world job laid out PASS-major -- sample index
-    # i = pass * (W*H*spp) + pixel * spp + s -- so every rank renders the whole film once (its own spp samples of every
-    # pixel, its own retry streams) and all ranks carry the same mix of vignetted and clear pixels.  (Pixel-major bands
-    # gave the ranks with the film's top and bottom rows 2.48 instead of 2.07 attempts per ray: 89 % efficiency at 8 GPUs
-    # from load imbalance alone, profiles/r01c_bench_headline_8gpu_bands.json.)
-    first = rank * n
-    samples = torch.empty((n, 4), dtype=torch.float32, device=dev)
-    tile = 1 << 28
-    for b in range(0, n, tile):
-        m = min(tile, n - b)
-        cam.synth_samples(wl.W, wl.H, wl.spp, wl.seed, first + b, m, out=samples[b:b + m])   # pixel index wraps per pass
-    rays = torch.empty((n, 8), dtype=torch.float32, device=dev)   # one 32-byte zoicb_ray per sample
-    torch.cuda.synchronize()
+    resident = (not args.stream) and n * 48 <= free * 0.9
+    tile = 1 << args.tile_log2
+    model = wl.params["lensModel"]
+
+    samples = rays = None
+    if resident:
+        samples = torch.empty((n, 4), dtype=torch.float32, device=dev)
+        for b in range(0, n, 1 << 28):
+            m = min(1 << 28, n - b)
+            cam.synth_samples(W, H, spp_pp, sseed, first + b, m, out=samples[b:b + m])
+        rays = torch.empty((n, 8), dtype=torch.float32, device=dev)   # one 32-byte zoicb_ray per sample
+        torch.cuda.synchronize()
+
+    job_results = []
 
     def step():
-        cam.create_rays(samples, seed=wl.seed, first_index=first, out=rays)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+        if resident:
+            cam.create_rays(samples, seed=wl.seed, first_index=first, out=rays)
+        else:
+            job_results.append(cam.run_job(W, H, spp_pp, sseed, wl.seed, first, n, tile=tile))
 
     for _ in range(args.warmup):
         step()
     barrier()
+    job_results.clear()
     cam.reset_stats()
     launches0 = zcam.kernel_launches()
     sampler = ClockSampler(local)
     sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    t_wall = time.perf_counter()
     ev0.record()
     for _ in range(args.steps):
         step()
     ev1.record()
     barrier()
+    wall_ms = 1e3 * (time.perf_counter() - t_wall)
     clocks = sampler.stop()
-    ms = ev0.elapsed_time(ev1)
     launches = zcam.kernel_launches() - launches0
-    stats = cam.stats()
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
-    ms_per_step = ms_max / args.steps
-    value = world * n / (ms_per_step * 1e-3) / 1e6
+    if resident:
+        ms = ev0.elapsed_time(ev1)          # CUDA events on the stream the kernels were launched on
+        stats = cam.stats()
+        kernel_ms = ms                      # one generate call per step: its duration is the step's
+        checksum = None
+    else:
+        ms = sum(r["device_ms"] for r in job_results)   # CUDA events inside zoicb_run_job, on its own streams
+        kernel_ms = sum(r["generate_ms"] for r in job_results)
+        stats = {k: sum(r["stats"][k] for r in job_results) for k in job_results[0]["stats"]}
+        checksum = job_results[-1]["checksum"]
+    ms_per_step = reduce_max(ms) / args.steps
+    value = sum(counts) / (ms_per_step * 1e-3) / 1e6
 
-    # roofline of the (single) kernel: its launch duration is the step duration (one launch per step)
-    model = wl.params["lensModel"]
+    # roofline of the dominant kernel (the generate kernel): algorithmic flops / bytes of a launch over its own duration
     flops = flops_per_batch(model, stats) / args.steps
-    kernel_s = (ms / args.steps) * 1e-3
+    kernel_s = (kernel_ms / args.steps) * 1e-3
     hbm_gbs = 48.0 * n / kernel_s / 1e9
     peaks = {}
     try:
@@ -295,29 +392,41 @@ def main():
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     hbm_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
-    # DRAM traffic per launch: dram__bytes_read.sum + dram__bytes_write.sum of the same kernel from the committed
-    # ncu capture (profiles/), scaled from the captured launch size to this launch (bytes per ray are size-independent)
-    traffic = None
+    # DRAM traffic per launch: dram__bytes_read.sum + dram__bytes_write.sum of the same kernel from the committed ncu
+    # capture (profiles/traffic.json, which names the commit it was taken at), scaled to this launch; refused (null) when
+    # the kernel source is newer than the capture
+    traffic, traffic_note = None, None
     try:
         cap = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        key = "kolb" if model == 1 else "thin"
+        key = "kolb" if model == 1 else ("thin_image" if wl.image() is not None else "thin")
         if key in cap:
-            traffic = cap[key]["dram_bytes_per_ray"] * n
+            src = os.path.join(ROOT, "zoic_b200", "csrc", cap[key].get("source", "kolb_pool2.cu"))
+            import hashlib
+            digest = hashlib.sha1(open(src, "rb").read()).hexdigest()[:12]
+            if cap[key].get("source_sha1", digest) == digest:
+                traffic = cap[key]["dram_bytes_per_ray"] * n
+                traffic_note = "ncu capture %s at commit %s" % (cap[key].get("capture"), cap[key].get("commit"))
+            else:
+                traffic_note = "profiles/traffic.json was captured for another version of %s: not used" % os.path.basename(src)
     except Exception:
         pass
+    per_launch = {"rays_per_launch": min(n, tile) if not resident else n,
+                  "duration": "CUDA events around the generate launches on their stream" + ("" if resident else " (zoicb_run_job, per tile)")}
     if model == 1:
         fp32_peak = zcam.measure_fp32_peak(local)
         roofline = {"bound": "fp32", "achieved": flops / kernel_s / 1e12, "peak": fp32_peak, "unit": "TFLOP/s",
-                    "frac": flops / kernel_s / 1e12 / fp32_peak, "traffic": traffic,
-                    "peak_source": "FFMA throughput measured live by zoicb_measure_fp32_peak (nominal 74.4 TFLOP/s at 1965 MHz)",
+                    "frac": flops / kernel_s / 1e12 / fp32_peak, "traffic": traffic, "traffic_source": traffic_note,
+                    "peak_source": "FFMA throughput measured live by zoicb_measure_fp32_peak (nominal 74.4 TFLOP/s at 1965 MHz); "
+                                   "MEASURED_PEAKS.json carries no fp32 figure",
                     "flops_per_ray": flops / n, "attempts_per_ray": stats["attempts"] / max(1, stats["rays"]),
                     "element_visits_per_ray": stats["element_visits"] / max(1, stats["rays"]),
                     "hbm": {"achieved": hbm_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_gbs / hbm_peak,
                             "peak_source": hbm_src, "bytes_per_ray": 48}}
     else:
         roofline = {"bound": "hbm", "achieved": hbm_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_gbs / hbm_peak,
-                    "traffic": traffic, "peak_source": hbm_src, "bytes_per_ray": 48,
+                    "traffic": traffic, "traffic_source": traffic_note, "peak_source": hbm_src, "bytes_per_ray": 48,
                     "attempts_per_ray": stats["attempts"] / max(1, stats["rays"])}
+    roofline.update(per_launch)
 
     # end to end through the host-buffer entry point: pinned host memory in, pinned host memory out
     e2e = None
@@ -325,7 +434,10 @@ def main():
         m = min(args.e2e_samples, n)
         hs = torch.empty((m, 4), dtype=torch.float32).pin_memory()
         hr = torch.empty((m, 8), dtype=torch.float32).pin_memory()
-        hs.copy_(samples[:m])
+        if resident:
+            hs.copy_(samples[:m])
+        else:
+            hs.copy_(cam.synth_samples(W, H, spp_pp, sseed, first, m))
         torch.cuda.synchronize()
         cam.create_rays_host(hs, seed=wl.seed, first_index=first, out=hr)  # warm-up (allocates staging)
         barrier()
@@ -334,81 +446,115 @@ def main():
         for _ in range(reps):
             cam.create_rays_host(hs, seed=wl.seed, first_index=first, out=hr)
         torch.cuda.synchronize()
-        dt = torch.tensor([(time.perf_counter() - t0) / reps], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-        e2e = {"value": world * m / float(dt.item()) / 1e6, "unit": UNIT, "h2d_bytes_per_step": 16 * m,
+        dt = reduce_max((time.perf_counter() - t0) / reps)
+        e2e = {"value": world * m / dt / 1e6, "unit": UNIT, "h2d_bytes_per_step": 16 * m,
                "d2h_bytes_per_step": 32 * m, "samples_per_step": m,
                "api": "zoicb_generate_host (pinned host buffers, 3-slot copy/compute pipeline)"}
         del hs, hr
-
-    # optional: generation + final gather of the ray buffer over NVLink (north_star's "final NCCL gather"), on a tile
-    gather = None
-    if world > 1 and args.gather:
-        from zoic_b200.distributed import gather_rays
-        m = min(1 << 26, n)
-        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        gather_rays(rays[:m])  # warm-up
-        barrier()
-        g0.record()
-        reps = 3
-        for _ in range(reps):
-            cam.create_rays(samples[:m], seed=wl.seed, first_index=first, out=rays[:m])
-            gather_rays(rays[:m])
-        g1.record()
-        barrier()
-        tg = torch.tensor([g0.elapsed_time(g1) / reps], dtype=torch.float64, device=dev)
-        dist.all_reduce(tg, op=dist.ReduceOp.MAX)
-        gather = {"value": world * m / (float(tg.item()) * 1e-3) / 1e6, "unit": UNIT, "rays_per_rank": m,
-                  "what": "generate + all-gather of the 32-byte ray records to every rank (NCCL), max over ranks"}
-        # the same with double-buffered tiles: the gather of tile k travels while tile k+1 is generated
         try:
-            from zoic_b200.distributed import TileGather
-            m2 = min(m, n // 2)
-            tiles = [rays[:m2], rays[m2:2 * m2]]
-            pipe = TileGather(m2, 8, torch.float32, dev)
-            reps = 6
-            for k in range(2):   # warm-up
-                pipe.wait(k & 1)
-                cam.create_rays(samples[:m2], seed=wl.seed, first_index=first, out=tiles[k & 1])
-                pipe.submit(k & 1, tiles[k & 1])
-            pipe.drain()
-            barrier()
-            g0.record()
-            for k in range(reps):
-                pipe.wait(k & 1)
-                cam.create_rays(samples[:m2], seed=wl.seed, first_index=first, out=tiles[k & 1])
-                pipe.submit(k & 1, tiles[k & 1])
-            pipe.drain()
-            g1.record()
-            barrier()
-            tp = torch.tensor([g0.elapsed_time(g1) / reps], dtype=torch.float64, device=dev)
-            dist.all_reduce(tp, op=dist.ReduceOp.MAX)
-            gather["pipelined"] = {"value": world * m2 / (float(tp.item()) * 1e-3) / 1e6, "unit": UNIT, "rays_per_rank": m2,
-                                   "what": "double-buffered tiles: all-gather of tile k overlaps the generation of tile k+1"}
-            del pipe
-        except Exception as exc:   # optional measurement: report, do not lose the bench line
-            gather["pipelined"] = {"error": repr(exc)}
+            y = pcie_yardstick(torch, dev, barrier, reduce_max)
+            per_rank_d2h = 32.0 * m / dt / 1e9
+            e2e["pcie"] = y
+            e2e["d2h_gbs_per_rank"] = per_rank_d2h
+            e2e["pcie_frac"] = per_rank_d2h / y["h2d_d2h_concurrent_each"]
+        except Exception as exc:   # a yardstick, not the measurement
+            e2e["pcie"] = {"error": repr(exc)}
+
+    # the whole job's GUARDED output against the EXACT mode's, every record, on the device (N = 1)
+    census = None
+    if world == 1 and args.census_rays and model == 1 and cam.mode == MODE_GUARDED:
+        m = min(n, args.census_rays)
+        t0 = time.perf_counter()
+        r = cam.run_job(W, H, spp_pp, sseed, wl.seed, first, m, tile=tile, census=True)
+        census = {"rays": r["census_rays"], "flips": r["census_flips"], "out_of_tol": r["census_out_of_tol"],
+                  "live": r["census_live"], "max_rel_origin": r["census_max_rel_origin"], "max_dir": r["census_max_dir"],
+                  "tol": 1e-5, "exact_reruns": r["stats"]["exact_reruns"], "seconds": time.perf_counter() - t0,
+                  "what": "every record of the first %d samples generated in GUARDED and in EXACT mode and compared on the "
+                          "device (weight and tries equal; live rays within tol)" % m}
+
+    # the same job WITH the final gather of every ray to rank 0 over NVLink
+    gather = None
+    if world > 1 and not args.no_gather:
+        gather = {"generate_only": value, "unit": UNIT, "consumer": 0, "records_per_rank_and_round": 1 << args.gather_tile_log2,
+                  "ingest_ceiling": {"value": 900e9 / 32 * world / (world - 1) / 1e6, "unit": UNIT,
+                                     "what": "NVLink 5 ingest of one GPU (900 GB/s nominal) / 32 B per ray, x G/(G-1): rank 0's own share does not travel"}}
+        gtile = 1 << args.gather_tile_log2
+
+        def gathered(transport, serial, slots, reps=2):
+            g = Gather(local, rank, world, 0, gtile, slots=slots, transport=transport)
+            try:
+                connect_gather(g)
+                best = None
+                for i in range(reps + 1):
+                    barrier()
+                    r = cam.run_job(W, H, spp_pp, sseed, wl.seed, first, n, gather=g, gather_counts=counts, serial=serial)
+                    msj = reduce_max(r["device_ms"])
+                    if i and (best is None or msj < best[0]):
+                        best = (msj, r)
+                barrier()
+                return best
+            finally:
+                g.close()
+
+        # what the consumer must see: the sum of every rank's own checksum
+        own = cam.run_job(W, H, spp_pp, sseed, wl.seed, first, n, tile=tile)
+        parts = [None] * world
+        dist.all_gather_object(parts, (own["checksum"], own["zero_weight"], own["tries_sum"]))
+        expect = (sum(p[0] for p in parts) % (1 << 64), sum(p[1] for p in parts), sum(p[2] for p in parts))
+        gather["expected_checksum"] = expect[0]
+        runs = [("sequential", "push", True, 1)] + [(t, t, False, 3) for t in args.transports.split(",") if t]
+        for name, transport, serial, slots in runs:
+            try:
+                msj, r = gathered(transport, serial, slots)
+                entry = {"value": sum(counts) / (msj * 1e-3) / 1e6, "unit": UNIT, "ms": msj, "transport": transport,
+                         "slots": slots}
+                if rank == 0:
+                    got = (r["checksum"], r["zero_weight"], r["tries_sum"])
+                    entry["checksum_ok"] = bool(got == expect and r["consumed"] == sum(counts))
+                    entry["ingest_gbs"] = 32.0 * (sum(counts) - n) / (msj * 1e-3) / 1e9
+                if name == "sequential":
+                    entry["what"] = "one stream, one round buffer: generate a round, push it, consume it, then the next"
+                    gather["sequential"] = entry
+                else:
+                    gather.setdefault("pipelined", {})[name] = entry
+            except Exception as exc:   # report, do not lose the bench line
+                gather.setdefault("errors", {})[name] = repr(exc)
+                barrier()
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        cpu = cpu_reference_rate(wl, args.cpu_samples)
-        cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
-        one = cpu_reference_rate(wl, max(args.cpu_samples // 16, 8192), cores=1)   # the 1-thread figure too
-        cpu["one_core"] = {"value": one["value"], "unit": UNIT, "sample": one["sample"]}
+        ref = CpuReference(wl)
+        ref.rate(max(args.cpu_samples // 8, 8192))
+        c = ref.rate(args.cpu_samples)
+        cpu = {k: c[k] for k in ("value", "unit", "cores", "kind", "sample", "seconds")}
+        ref.close()
+        one = CpuReference(wl, cores=1)   # the 1-thread figure and the plugin as shipped
+        o = one.rate(max(args.cpu_samples // 16, 8192))
+        cpu["one_core"] = {"value": o["value"], "unit": UNIT, "sample": o["sample"]}
+        if c["kind"] == "reference":
+            s = one.rate(max(args.cpu_samples // 16, 8192), threads=os.cpu_count() or 1)
+            cpu["as_shipped"] = {"value": s["value"], "unit": UNIT, "threads": s["cores"], "sample": s["sample"]}
+        one.close()
 
     if rank == 0:
-        cfg = wl.describe()
-        cfg.update({"samples_per_gpu_per_step": n, "arithmetic_mode": mode_name,
-                    "l2": ("inputs (%.1f GB per step) are larger than L2; no flush needed" % (16.0 * n / 1e9)) if 16.0 * n > 2.6e8
-                          else "batch (%.0f MB in + out) fits in L2: the number is L2-assisted" % (48.0 * n / 1e6),
-                    "sharding": "rank r owns samples [r*n,(r+1)*n) of a %dx%dx%d-spp job in %d pass-major passes of %d spp: "
-                                "every rank renders the whole film, no data-path collective" % (wl.W, wl.H, wl.spp * world, world, wl.spp)})
+        run = {"samples_per_gpu_per_step": n, "first_sample_of_rank0": first, "arithmetic_mode": mode_name,
+               "residency": "resident: samples and rays of the rank's share live in HBM, one zoicb_generate per step" if resident
+                            else "streamed: zoicb_run_job, tiles of %d samples synthesised on the device -> generated -> consumed (checksum)" % tile,
+               "l2": ("inputs (%.1f GB per step) are larger than L2; no flush needed" % (16.0 * n / 1e9)) if 16.0 * n > 2.6e8
+                     else "batch (%.0f MB in + out) fits in L2: the number is L2-assisted" % (48.0 * n / 1e6),
+               "sharding": "strong: rank r owns samples [r N/G, (r+1) N/G) of the one %dx%dx%d job (%s split); no data-path "
+                           "collective in `value`" % (wl.W, wl.H, wl.spp, split),
+               "wall_ms_per_step": reduce_max(wall_ms) / args.steps if world == 1 else None,
+               "create": create_times}
+        if checksum is not None:
+            run["checksum"] = checksum
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg, "clocks": clocks,
-                "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+                "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": wl.describe(), "run": run,
+                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
                 "stats": stats}
+        if census:
+            line["parity_census"] = census
         if gather:
             line["gather"] = gather
         emit(line)

@@ -57,6 +57,8 @@ def load(draw=False, plugin=None):
         host.zref_create.argtypes = [C.c_int, C.POINTER(RefParams), C.c_void_p, C.c_int, C.c_int, C.c_int]
         host.zref_generate.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64,
                                        C.c_void_p, C.c_void_p, C.c_void_p]
+        host.zref_generate_mt.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64,
+                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         host.zref_generate_one_with_state.argtypes = [C.c_void_p] * 6
         host.zref_destroy.argtypes = [C.c_void_p]
         host.zref_log.restype = C.c_char_p
@@ -116,14 +118,20 @@ class RefCamera:
     def aborted(self):
         return bool(self.h.zref_aborted(self.c))
 
-    def generate(self, samples, seed=0, first_index=0):
+    def generate(self, samples, seed=0, first_index=0, nthreads=0):
+        """CreateRay per sample; nthreads > 0: that many threads share this ONE node, as Arnold's render threads do
+        (the reference's unsynchronised shared counters included; same rays, the retry RNG is interposed per thread)."""
         s = np.ascontiguousarray(samples, dtype=np.float32).reshape(-1, 4)
         n = s.shape[0]
         o = np.empty((n, 4), np.float32)
         d = np.empty((n, 4), np.float32)
         st = np.zeros(3, np.uint64)
-        self.h.zref_generate(self.c, s.ctypes.data, n, first_index, seed, o.ctypes.data, d.ctypes.data,
-                             st.ctypes.data)
+        if nthreads > 0:
+            self.h.zref_generate_mt(self.c, s.ctypes.data, n, first_index, seed, o.ctypes.data, d.ctypes.data,
+                                    st.ctypes.data, int(nthreads))
+        else:
+            self.h.zref_generate(self.c, s.ctypes.data, n, first_index, seed, o.ctypes.data, d.ctypes.data,
+                                 st.ctypes.data)
         return o, d, {"success": int(st[0]), "vignetted": int(st[1]), "attempts": int(st[2])}
 
     def generate_one(self, sample, state):

@@ -20,6 +20,7 @@
 #include <dlfcn.h>
 #include <map>
 #include <string>
+#include <thread>
 #include <vector>
 
 // ------------------------------------------------------------------------------------------------
@@ -240,12 +241,12 @@ const char* zref_log(const zref_camera* c) { return c->log.c_str(); }
 // samples: n x (sx, sy, lensx, lensy).  Outputs: origin_w n x (ox, oy, oz, weight), dir_tries n x (dx, dy, dz, tries).
 // `first_index` is the global index of samples[0] (the retry stream is seeded from seed and the global index).
 // stats (may be NULL): [0] rays with weight != 0 ... exactly: [0] success, [1] vignetted (zero weight), [2] attempts.
-void zref_generate(zref_camera* c, const float* samples, uint64_t n, uint64_t first_index, uint64_t seed,
-                   float* origin_w, float* dir_tries, uint64_t* stats) {
+static void generate_range(zref_camera* c, const float* samples, uint64_t begin, uint64_t end, uint64_t first_index,
+                           uint64_t seed, float* origin_w, float* dir_tries, uint64_t* stats) {
     g_current = &c->node;
     g_log = nullptr;
     uint64_t ok = 0, vig = 0, attempts = 0;
-    for (uint64_t i = 0; i < n; ++i) {
+    for (uint64_t i = begin; i < end; ++i) {
         AtCameraInput in;
         in.sx = samples[4 * i + 0];
         in.sy = samples[4 * i + 1];
@@ -272,6 +273,31 @@ void zref_generate(zref_camera* c, const float* samples, uint64_t n, uint64_t fi
         if (out.weight.r == 0.0f) ++vig; else ++ok;
     }
     if (stats) { stats[0] = ok; stats[1] = vig; stats[2] = attempts; }
+}
+
+void zref_generate(zref_camera* c, const float* samples, uint64_t n, uint64_t first_index, uint64_t seed,
+                   float* origin_w, float* dir_tries, uint64_t* stats) {
+    generate_range(c, samples, 0, n, first_index, seed, origin_w, dir_tries, stats);
+}
+
+// The plugin "as shipped": `nthreads` render threads call CreateRay on ONE node at the same time, like Arnold's render
+// threads do.  The reference's counters (succesRays, vignettedRays, ... src/zoic.cpp:533-534) are plain
+// members of the node's shared data, incremented without synchronisation by every thread -- one contended cache line;
+// its retry RNG is interposed per thread here, so the rays themselves still equal the single-thread run.
+void zref_generate_mt(zref_camera* c, const float* samples, uint64_t n, uint64_t first_index, uint64_t seed,
+                      float* origin_w, float* dir_tries, uint64_t* stats, int nthreads) {
+    if (nthreads < 1) nthreads = 1;
+    std::vector<std::thread> pool;
+    std::vector<uint64_t> part((size_t)nthreads * 3, 0);
+    for (int t = 0; t < nthreads; ++t) {
+        const uint64_t b = n * (uint64_t)t / (uint64_t)nthreads, e = n * (uint64_t)(t + 1) / (uint64_t)nthreads;
+        pool.emplace_back(generate_range, c, samples, b, e, first_index, seed, origin_w, dir_tries, &part[(size_t)t * 3]);
+    }
+    for (auto& th : pool) th.join();
+    if (stats) {
+        stats[0] = stats[1] = stats[2] = 0;
+        for (int t = 0; t < nthreads; ++t) for (int k = 0; k < 3; ++k) stats[k] += part[(size_t)t * 3 + k];
+    }
 }
 
 // One CreateRay with an explicit retry stream made of the given draws (for pinning the argument

@@ -105,6 +105,7 @@ __global__ void wait_kernel(const unsigned long long* flags, int count, int skip
                             unsigned long long* error, unsigned long long timeout_ns) {
     const int i = threadIdx.x;
     if (i >= count || i == skip) return;
+    if (ld_acquire_sys(error)) return;   // a wait already failed: do not add another time-out to the first
     const unsigned long long t0 = global_ns();
     while (ld_acquire_sys(flags + i) < value) {
         if (global_ns() - t0 > timeout_ns) { atomicExch(error, 1ull); return; }
@@ -147,7 +148,7 @@ struct zoicb_gather {
     uint64_t base = 0, job_base = 0, job_rounds = 0;   // rounds of all earlier jobs; of the current / last job
     NcclComm comm = nullptr;
     bool own_comm = false;
-    unsigned long long timeout_ns = 20ull * 1000 * 1000 * 1000;
+    unsigned long long timeout_ns = 10ull * 1000 * 1000 * 1000;   // ZOICB_GATHER_TIMEOUT_S overrides
 
     bool is_consumer() const { return rank == consumer; }
     // `round` counts from the start of the current job; slots rotate on the global round number
