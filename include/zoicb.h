@@ -12,6 +12,7 @@
  *   zoicb_get_stats     the counters printed by node_finish      src/zoic.cpp:1729-1732
  *   zoicb_destroy       node_finish                              src/zoic.cpp:1723-1749
  *   zoicb_transform_rays  (the renderer's camera-to-world step after camera_create_ray; nothing in zoic)
+ *   zoicb_differentials   the ray derivatives zoic leaves as a TODO / fakes                 src/zoic.cpp:12-13, 1971-1977
  *   zoicb_write_draw_file writeToFile + the DRAW_ONLY ray dumps  src/zoic.cpp:1240-1293, 1121-1128, 1146-1153
  *   zoicb_params        the 14 node parameters                   src/zoic.cpp:1547-1562
  *   zoicb_run_job       the renderer's loop over camera_create_ray for a whole W x H x spp frame (nothing in zoic: Arnold
@@ -177,6 +178,20 @@ ZOICB_API zoicb_status zoicb_generate_one(zoicb_ctx* ctx, const float* sample, u
  * Arithmetic: one fma chain per component, innermost term first (zoic_b200/csrc/kernels.cu). */
 ZOICB_API zoicb_status zoicb_transform_rays(zoicb_ctx* ctx, const zoicb_ray* d_rays, uint64_t n, const float* m3x4,
                                             zoicb_ray* d_out, void* stream);
+
+/* Ray differentials: the AtCameraOutput fields the reference leaves unset (TODO at src/zoic.cpp:12-13)
+ * and fakes with "if (tries > 0) dOdy = origin, dDdy = dir" (:1971-1977).  For every sample, the derivative of its ray
+ * with respect to the screen position at a FIXED aperture point, as forward differences over one pixel: dsx / dsy are
+ * the screen-space extent of a pixel (AtCameraInput::dsx / dsy).  d_samples, first_index and rng_seed are those of the
+ * zoicb_generate call that produced d_rays (its weight and tries select the accepted attempt).  Zero-weight rays and
+ * neighbours that are stopped inside the lens get zero vectors.  Exact arithmetic; the full contract is stated in
+ * zoic_b200/csrc/differentials.cu and, for the CPU, in oracle/zoic_port.cpp (zport_differentials). */
+typedef struct zoicb_ray_diff {
+    float dOdx[3], dOdy[3], dDdx[3], dDdy[3];
+} zoicb_ray_diff;
+ZOICB_API zoicb_status zoicb_differentials(zoicb_ctx* ctx, const void* d_samples, uint64_t n, uint64_t first_index,
+                                           uint64_t rng_seed, float dsx, float dsy, const zoicb_ray* d_rays,
+                                           zoicb_ray_diff* d_out, void* stream);
 
 /* draw.zoic writer: the file the reference's -D_DRAW build leaves for src/draw.py
  * (writeToFile, src/zoic.cpp:1240-1293, and the DRAW_ONLY blocks of traceThroughLensElements :1121-1128,

@@ -51,6 +51,8 @@ def load():
                                         C.c_void_p]
     lib.zport_sample_stream.argtypes = [C.c_uint64, C.c_uint64, C.c_void_p]
     lib.zport_transform_rays.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
+    lib.zport_differentials.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_float, C.c_float,
+                                        C.c_void_p, C.c_void_p, C.c_void_p]
     lib.zport_get_constants.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
     lib.zport_get_bokeh_tables.argtypes = [C.c_void_p] * 5
     _lib = lib
@@ -114,6 +116,17 @@ class PortCamera:
                                 st.ctypes.data, nthreads)
         keys = ("success", "vignetted", "attempts", "element_visits", "tir")
         return o, d, {k: int(v) for k, v in zip(keys, st)}
+
+    def differentials(self, samples, rays, dsx, dsy, seed=0, first_index=0):
+        """CPU statement of the ray-differential contract (include/zoicb.h: zoicb_differentials): [n, 12] floats
+        (dOdx, dOdy, dDdx, dDdy) for samples [n, 4] whose generated records are rays [n, 8]."""
+        s = np.ascontiguousarray(samples, dtype=np.float32).reshape(-1, 4)
+        r = np.ascontiguousarray(rays, dtype=np.float32).reshape(-1, 8)
+        tries, weight = np.ascontiguousarray(r[:, 7]), np.ascontiguousarray(r[:, 3])
+        out = np.empty((s.shape[0], 12), np.float32)
+        self.lib.zport_differentials(self.c, s.ctypes.data, s.shape[0], first_index, seed, C.c_float(dsx), C.c_float(dsy),
+                                     tries.ctypes.data, weight.ctypes.data, out.ctypes.data)
+        return out
 
     def generate_one(self, sample, state):
         s = np.asarray(sample, np.float32)

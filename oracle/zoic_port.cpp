@@ -810,6 +810,119 @@ void zport_transform_rays(const float* rays, uint64_t n, const float* m, float* 
     }
 }
 
+// Ray differentials (the reference's open TODO, src/zoic.cpp:12-13, and its stand-in hack :1971-1977
+// "if (tries > 0) dOdy = origin, dDdy = dir").  CPU statement of the contract of zoicb_differentials (include/zoicb.h):
+// the derivative of the generated ray with respect to the screen position AT A FIXED POINT OF THE APERTURE, as forward
+// differences over one pixel (dsx, dsy = Arnold's AtCameraInput::dsx / dsy):
+//   1. a sample whose ray has weight 0 gets four zero vectors;
+//   2. the aperture draw of the ACCEPTED attempt is (lensx, lensy) when tries == 0, otherwise the tries-th pair of the
+//      sample's retry stream; it is mapped to its aim point exactly like createRay maps it (thin lens: lens point
+//      (lx R, ly R, 0); raytraced: scaled / translated / rotated by the exit-pupil LUT of the sample's OWN film point,
+//      with the retry arithmetic of :1933 when tries > 0);
+//   3. the base ray (sx, sy), the x-neighbour (fl(sx + dsx), sy) and the y-neighbour (sx, fl(sy + dsy)) each run from
+//      their film point through that one aim point: thin lens -- dir = normalize(focus(p') - lens point), origin = lens
+//      point; raytraced -- (aim - film', -thickness0) marched through the stack with traceThroughLensElements, both
+//      vectors negated like the reference's output;
+//   4. dOdx = origin_x - origin_base, dDdx = dir_x - dir_base (component-wise fp32 subtractions), likewise for y; a
+//      neighbour that is stopped inside the lens gives zero vectors for its axis.
+// diffs: n x 12 floats (dOdx, dOdy, dDdx, dDdy).
+void zport_differentials(void* c, const float* samples, uint64_t n, uint64_t first_index, uint64_t seed, float dsx, float dsy,
+                         const float* tries_in, const float* weight_in, float* diffs) {
+    const Camera* cam = (const Camera*)c;
+    const Params& params = cam->params;
+    const Lensdata& ld = cam->lens;
+    for (uint64_t i = 0; i < n; ++i) {
+        float* out = diffs + 12 * i;
+        for (int k = 0; k < 12; ++k) out[k] = 0.0f;
+        if (weight_in[i] == 0.0f) continue;
+        const float sx = samples[4 * i], sy = samples[4 * i + 1];
+        float u = samples[4 * i + 2], v = samples[4 * i + 3];
+        const int tries = (int)tries_in[i];
+        if (tries > 0) {
+            Xor128 rng = sample_stream(seed, first_index + i);
+            for (int t = 0; t < tries; ++t) {
+                uint32_t k1 = xor128(rng), k2 = xor128(rng);  // first draw -> second parameter
+                v = (float)k1 / 4294967296.0f;
+                u = (float)k2 / 4294967296.0f;
+            }
+        }
+        float lx = 0, ly = 0;
+        if (!params.useImage) concentricDiskSample(u, v, &lx, &ly);
+        else cam->image.bokehSample(u, v, &lx, &ly);
+        V3 o[3], d[3];
+        bool ok[3] = {true, true, true};
+        const float fsx[3] = {sx, sx + dsx, sx}, fsy[3] = {sy, sy, sy + dsy};
+        if (params.lensModel == THINLENS) {
+            for (int k = 0; k < 3; ++k) {
+                V3 p = v3(fsx[k] * cam->tan_fov, fsy[k] * cam->tan_fov, 1.0);
+                d[k] = normalize(p);
+                o[k] = v3(0, 0, 0);
+                if (params.useDof) {
+                    o[k] = v3(lx * cam->apertureRadius, ly * cam->apertureRadius, 0.0);
+                    float intersection = std::fabs(params.focalDistance / d[k].z);
+                    V3 focusPoint = mul(d[k], intersection);
+                    d[k] = normalize(sub(focusPoint, o[k]));
+                }
+                d[k].z *= -1.0;
+            }
+        } else {
+            const float half = (float)((double)params.sensorWidth * 0.5);
+            const float ap0 = ld.lenses[0].aperture, th0 = ld.lenses[0].thickness;
+            float ax, ay;
+            {
+                V3 origin = v3((float)((double)sx * ((double)params.sensorWidth * 0.5)),
+                               (float)((double)sy * ((double)params.sensorWidth * 0.5)), ld.originShift);
+                if (!params.kolbSamplingLUT) {
+                    ax = lx * ap0; ay = ly * ap0;
+                } else {  // the LUT arithmetic of createRay, :1889-1948
+                    float samplingErrorCorrection = 1.05;
+                    float distanceFromOrigin = std::fabs(std::sqrt(origin.x * origin.x + origin.y * origin.y));
+                    const int nk = (int)ld.lutKey.size();
+                    int low = (int)(std::lower_bound(ld.lutKey.begin(), ld.lutKey.end(), distanceFromOrigin) - ld.lutKey.begin());
+                    if (low >= nk) low = nk - 1;
+                    float lowerBound = ld.lutKey[low];
+                    float theta = (float)atan2((double)origin.y, (double)origin.x);
+                    float sin = fastSin(theta), cos = fastCos(theta);
+                    float maxScale, translation;
+                    if (low == 0) {
+                        maxScale = ld.lutBox[0].maxScale() * samplingErrorCorrection;
+                        translation = ld.lutBox[0].centroidX();
+                    } else {
+                        int prv = low - 1;
+                        float prev = ld.lutKey[prv];
+                        float percentage = (distanceFromOrigin - lowerBound) / (prev - lowerBound);
+                        maxScale = linearInterpolate(percentage, ld.lutBox[low].maxScale(), ld.lutBox[prv].maxScale()) * samplingErrorCorrection;
+                        translation = linearInterpolate(percentage, ld.lutBox[low].centroidX(), ld.lutBox[prv].centroidX());
+                    }
+                    lx *= maxScale; ly *= maxScale;
+                    lx += translation;
+                    if (tries > 0) ly += translation;   // :1933
+                    ax = lx * cos - ly * sin;
+                    ay = lx * sin + ly * cos;
+                }
+            }
+            (void)half;
+            for (int k = 0; k < 3; ++k) {
+                o[k] = v3((float)((double)fsx[k] * ((double)params.sensorWidth * 0.5)),
+                          (float)((double)fsy[k] * ((double)params.sensorWidth * 0.5)), ld.originShift);
+                d[k] = v3(ax - o[k].x, ay - o[k].y, -th0);
+                ok[k] = traceThroughLensElements(&o[k], &d[k], &ld, nullptr);
+                d[k] = mul(d[k], -1.0);
+                o[k] = mul(o[k], -1.0);
+            }
+        }
+        if (!ok[0]) continue;   // cannot happen for a consistent (tries, weight): the accepted attempt passes
+        if (ok[1]) {
+            V3 a = sub(o[1], o[0]), b = sub(d[1], d[0]);
+            out[0] = a.x; out[1] = a.y; out[2] = a.z; out[6] = b.x; out[7] = b.y; out[8] = b.z;
+        }
+        if (ok[2]) {
+            V3 a = sub(o[2], o[0]), b = sub(d[2], d[0]);
+            out[3] = a.x; out[4] = a.y; out[5] = a.z; out[9] = b.x; out[10] = b.y; out[11] = b.z;
+        }
+    }
+}
+
 // Derived camera state for host-side parity tests.
 //   scalars[16]: fov, tan_fov, apertureRadius, userApertureRadius, originShift, apertureDistance,
 //                focalLengthRatio, tracedFocalLength[0..1], principalPlane[0..1], focalPoint[0..1],

@@ -130,6 +130,63 @@ def test_census_counts_what_it_should(port):
 
 
 # ---------------------------------------------------------------------------------------------------
+# ray differentials: the derivatives the reference leaves as a TODO (src/zoic.cpp:12-13, :1971-1977)
+# ---------------------------------------------------------------------------------------------------
+def test_ray_differentials_match_the_contract(port):
+    """zoicb_differentials against the CPU statement of its contract (oracle/zoic_port.cpp: zport_differentials), bit for
+    bit, for both lens models, with and without LUT / image / depth of field; rays from the default (GUARDED) mode and
+    from EXACT mode give the same differentials (they agree on weight and tries); zero-weight rays get zeros; a zero step
+    gives zeros; a thin lens without depth of field has the analytic pinhole derivative."""
+    from zoic_b200 import ZoicCamera, MODE_EXACT
+    from zoic_b200.synth import hex_bokeh_image
+    from zoic_b200.workloads import lens_path
+    cases = [
+        (dict(lensModel=1, lensDataPath=lens_path("double_gauss_f2.0.dat"), focalLength=5.0, fStop=2.0), None),
+        (dict(lensModel=1, lensDataPath=lens_path("fisheye_muller_f4.0.dat"), focalLength=1.0, fStop=4.0), None),
+        (dict(lensModel=1, lensDataPath=lens_path("tessar_f2.8.dat"), focalLength=5.0, fStop=2.8, kolbSamplingLUT=0, useImage=1), 65),
+        (dict(lensModel=0, focalLength=3.5, fStop=2.8, opticalVignettingDistance=2.0, useImage=1), 255),
+        (dict(lensModel=0, focalLength=3.5, fStop=2.8, opticalVignettingDistance=4.0, opticalVignettingRadius=0.6), None),
+        (dict(lensModel=0, focalLength=3.5, fStop=2.8, useDof=0), None),
+    ]
+    W, H, spp, n, first = 640, 360, 16, 150_001, 77_777
+    dsx, dsy = 2.0 / W, 2.0 / W            # one pixel in screen space (sy spans the aspect-scaled range at the same pitch)
+    for kw, img in cases:
+        image = hex_bokeh_image(img) if img else None
+        cam = ZoicCamera(image=image, **kw)
+        ref = port.PortCamera(image=image, **kw)
+        s = cam.synth_samples(W, H, spp, 9, first, n)
+        rays = cam.create_rays(s, seed=5, first_index=first)
+        got = cam.differentials(s, rays, dsx, dsy, seed=5, first_index=first)
+        torch.cuda.synchronize()
+        hs, hr = s.cpu().numpy(), rays.cpu().numpy()
+        want = ref.differentials(hs, hr, dsx, dsy, seed=5, first_index=first)
+        assert bits_equal(got.cpu().numpy(), want), kw
+        dead = hr[:, 3] == 0
+        assert not want[dead].any()
+        live = ~dead
+        assert np.isfinite(want).all() and np.abs(want[live, 6:]).max() < 0.05     # a pixel's worth of direction change
+        assert (np.abs(want[live, 6:9]).sum(1) > 0).mean() > 0.95                   # and almost never stopped
+        cam.set_mode(MODE_EXACT)
+        rays_x = cam.create_rays(s, seed=5, first_index=first)
+        got_x = cam.differentials(s, rays_x, dsx, dsy, seed=5, first_index=first)
+        assert torch.equal(got.view(torch.int32), got_x.view(torch.int32))
+        assert not cam.differentials(s, rays, 0.0, 0.0, seed=5, first_index=first).any()
+        if kw.get("useDof", 1) == 0:
+            # pinhole: dir = normalize(sx t, sy t, 1) flipped in z; d dir / d sx by forward difference in float64
+            c = cam.constants()
+            t = float(c["tan_fov"])
+            p0 = np.stack([hs[:, 0].astype(np.float64) * t, hs[:, 1].astype(np.float64) * t, np.ones(n)], 1)
+            p1 = p0.copy()
+            p1[:, 0] = (hs[:, 0].astype(np.float64) + dsx) * t
+            d0 = p0 / np.linalg.norm(p0, axis=1, keepdims=True)
+            d1 = p1 / np.linalg.norm(p1, axis=1, keepdims=True)
+            an = (d1 - d0) * np.array([1, 1, -1.0])
+            assert np.abs(want[:, 6:9] - an).max() < 5e-7 and not want[:, :6].any()
+        cam.close()
+        ref.close()
+
+
+# ---------------------------------------------------------------------------------------------------
 # BASELINE.json's full sizes, streamed (SURVEY.md 8(d): "Config 4/5 ... streamed in tiles")
 # ---------------------------------------------------------------------------------------------------
 def _full_size_names():
@@ -210,14 +267,23 @@ def test_lut_box_fold_rearm_quirk_on_the_gpu():
         draws[5, pos] = (quarter, three)
         accept[5, pos] = 1
     accept[7, :] = 0                                           # nothing accepted: the box stays at the origin
+    # films 8..11: a LATE re-arm that changes the final box.  Only candidates with x > -0.2 ap and y > 0.6 ap are accepted,
+    # so the crafted candidate (-ap/2, +ap/2) becomes the minimum in x AND in y; the minima cancel and the next accepted
+    # candidate re-arms the box, which forgets every extreme seen before (lane positions around the device kernel's chunks)
+    u = draws.astype(np.float32) * np.float32(2.0 ** -32)
+    p = (u * np.float32(2.0) - np.float32(1.0)) * np.float32(ap)
+    for f, pos in zip(range(8, 12), (2500, 2528, 2559, 2560)):
+        accept[f] = ((p[f, :, 0] > -0.2 * ap) & (p[f, :, 1] > 0.6 * ap)).astype(np.uint8)
+        draws[f, pos] = (quarter, three)
+        accept[f, pos] = 1
     dev, host = debug_lut_boxes(draws, accept, n_film, per_film, ap, device=0)
     assert bits_equal(dev, host)
     assert not host[7].any() and host[1:7].any()
-    # the re-arm really happened somewhere: a plain min / max over the accepted points differs from the fold
+    # the late re-arm really happened: the crafted candidate is the plain minimum in x, the fold has forgotten it
     u = draws.astype(np.float32) * np.float32(2.0 ** -32)
     p = (u * np.float32(2.0) - np.float32(1.0)) * np.float32(ap)
-    plain = np.stack([np.where(accept == 1, p[..., 0], np.inf).min(1), np.where(accept == 1, p[..., 1], np.inf).min(1)], 1)
-    assert (plain[:7] != host[:7, :2]).any()
+    plain_minx = np.where(accept == 1, p[..., 0], np.inf).min(1)
+    assert (plain_minx[8:12] == np.float32(-0.5) * np.float32(ap)).all() and (host[8:12, 0] > plain_minx[8:12]).all()
 
 
 # ---------------------------------------------------------------------------------------------------

@@ -353,7 +353,7 @@ def test_large_batch_spans_many_chunks_and_keeps_counters(port):
     assert not torch.isnan(o[:, 3]).any() and not torch.isnan(d[:, 3]).any()
     assert st["rays"] == n and st["success"] + st["vignetted"] == n
     assert st["success"] == int((o[:, 3] != 0).sum()) and st["vignetted"] == int((o[:, 3] == 0).sum())
-    assert st["attempts"] == n + int(d[:, 3].sum())
+    assert st["attempts"] == n + int(d[:, 3].sum(dtype=torch.float64))
     cam.close()
 
 

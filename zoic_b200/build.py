@@ -14,7 +14,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.environ.get("ZOICB_LIBDIR") or os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libzoicb.so")
 
-SOURCES = ["capi.cu", "kernels.cu", "kolb_pool2.cu", "bokeh_build.cu", "job.cu", "gather.cu", "host_setup.cpp"]
+SOURCES = ["capi.cu", "kernels.cu", "kolb_pool2.cu", "bokeh_build.cu", "job.cu", "gather.cu", "differentials.cu", "host_setup.cpp"]
 ADAPTER = "arnold_adapter.cpp"
 PLUGIN = os.path.join(LIBDIR, "libzoic_arnold.so")
 HEADERS = ["camera_state.h", "lens_math.cuh", "host_setup.h", "kernels.h", "kernel_common.cuh", "gnu_sort.h",

@@ -205,6 +205,22 @@ class ZoicCamera:
                                                  C.c_void_p(stream)))
         return out
 
+    def differentials(self, samples, rays, dsx, dsy, seed=0, first_index=0, out=None, stream=None):
+        """Ray differentials: [n, 12] floats (dOdx, dOdy, dDdx, dDdy) for the samples [n, 4] whose
+        generated records are rays [n, 8]; seed / first_index as in the create_rays call that made them."""
+        import torch
+        assert samples.is_cuda and rays.is_cuda and samples.is_contiguous() and rays.is_contiguous()
+        assert samples.dtype == torch.float32 and rays.dtype == torch.float32
+        n = samples.numel() // 4
+        assert rays.numel() == 8 * n
+        if out is None:
+            out = torch.empty((n, 12), dtype=torch.float32, device=samples.device)
+        if stream is None:
+            stream = torch.cuda.current_stream(samples.device).cuda_stream
+        capi.check(self.lib.zoicb_differentials(self.ctx, samples.data_ptr(), n, first_index, seed, float(dsx), float(dsy),
+                                                rays.data_ptr(), out.data_ptr(), C.c_void_p(stream)))
+        return out
+
     def synth_samples(self, W, H, spp, seed, first_index, n, out=None, stream=None):
         """Synthetic (sx, sy, lensx, lensy) samples generated on the device."""
         import torch

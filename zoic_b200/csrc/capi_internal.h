@@ -42,6 +42,11 @@ struct zoicb_ctx {
     std::mutex host_mu;
     // optional: events recorded around the device-side bokeh table build (zoicb_build_bokeh_tables)
     cudaEvent_t bokeh_ev0 = nullptr, bokeh_ev1 = nullptr;
+    // buffers, streams and events of zoicb_run_job, kept between jobs (allocating and freeing tens of GB per job cost
+    // more than a small job itself); one job at a time per context
+    std::mutex job_mu;
+    void* job_cache = nullptr;
+    void (*job_cache_free)(void*) = nullptr;
     // wall time of the creation pipeline (zoicb_get_create_times)
     double create_ms = 0.0, lut_ms = 0.0, bokeh_ms = 0.0;
 };

@@ -142,7 +142,10 @@ cudaError_t launch_consume(const RayRecord* rays, uint64_t n, void* d_totals, cu
 
 namespace {
 
+// Everything a job allocates, kept in the context between jobs and grown on demand.
 struct JobBuffers {
+    uint64_t cap_samples = 0, cap_rays = 0, cap_exact = 0, cap_queue = 0;
+    int n_samples = 0, n_rays = 0;
     float4* samples[2] = {nullptr, nullptr};
     RayRecord* rays[3] = {nullptr, nullptr, nullptr};
     RayRecord* exact = nullptr;
@@ -151,22 +154,70 @@ struct JobBuffers {
     ConsumeTotals* consume = nullptr;
     CensusTotals* census = nullptr;
     cudaStream_t s_syn = nullptr, s_gen = nullptr, s_con = nullptr;
-    std::vector<cudaEvent_t> events;
+    std::vector<cudaEvent_t> plain, timed;   // event pools, handed out per job
+    size_t next_plain = 0, next_timed = 0;
     ~JobBuffers() {
         for (auto p : samples) cudaFree(p);
         for (auto p : rays) cudaFree(p);
         cudaFree(exact); cudaFree(stats); cudaFree(consume); cudaFree(census);
         cudaFree(ws.counters); cudaFree(ws.queue);
         for (auto s : {s_syn, s_gen, s_con}) if (s) cudaStreamDestroy(s);
-        for (auto e : events) cudaEventDestroy(e);
+        for (auto e : plain) cudaEventDestroy(e);
+        for (auto e : timed) cudaEventDestroy(e);
     }
-    cudaEvent_t event(unsigned flags = cudaEventDisableTiming) {
-        cudaEvent_t e = nullptr;
-        cudaEventCreateWithFlags(&e, flags);
-        events.push_back(e);
-        return e;
+    void begin_job() { next_plain = next_timed = 0; }
+    cudaEvent_t event(bool timing = false) {
+        std::vector<cudaEvent_t>& pool = timing ? timed : plain;
+        size_t& next = timing ? next_timed : next_plain;
+        if (next == pool.size()) {
+            cudaEvent_t e = nullptr;
+            cudaEventCreateWithFlags(&e, timing ? cudaEventDefault : cudaEventDisableTiming);
+            pool.push_back(e);
+        }
+        return pool[next++];
+    }
+    // device memory for a job: `nsmp` sample tiles and `nray` ray tiles of `cap` entries (+ one for the census)
+    cudaError_t ensure(uint64_t cap, int nsmp, int nray, bool census_pass) {
+        cudaError_t e;
+        if (!s_gen) {
+            if ((e = cudaStreamCreateWithFlags(&s_syn, cudaStreamNonBlocking)) != cudaSuccess) return e;
+            if ((e = cudaStreamCreateWithFlags(&s_gen, cudaStreamNonBlocking)) != cudaSuccess) return e;
+            if ((e = cudaStreamCreateWithFlags(&s_con, cudaStreamNonBlocking)) != cudaSuccess) return e;
+            if ((e = cudaMalloc(&stats, 2 * sizeof(DeviceStats))) != cudaSuccess) return e;
+            if ((e = cudaMalloc(&consume, sizeof(ConsumeTotals))) != cudaSuccess) return e;
+            if ((e = cudaMalloc(&census, sizeof(CensusTotals))) != cudaSuccess) return e;
+            if ((e = cudaMalloc(&ws.counters, 4 * sizeof(unsigned long long))) != cudaSuccess) return e;
+        }
+        if (cap > cap_samples || nsmp > n_samples) {
+            for (auto& p : samples) { cudaFree(p); p = nullptr; }
+            cap_samples = 0;
+            const uint64_t c = cap > cap_samples ? cap : cap_samples;
+            for (int i = 0; i < nsmp; ++i) if ((e = cudaMalloc(&samples[i], c * sizeof(float4))) != cudaSuccess) return e;
+            cap_samples = c; n_samples = nsmp;
+        }
+        if (nray > 0 && (cap > cap_rays || nray > n_rays)) {
+            for (auto& p : rays) { cudaFree(p); p = nullptr; }
+            cap_rays = 0;
+            for (int i = 0; i < nray; ++i) if ((e = cudaMalloc(&rays[i], cap * sizeof(RayRecord))) != cudaSuccess) return e;
+            cap_rays = cap; n_rays = nray;
+        }
+        if (census_pass && cap > cap_exact) {
+            cudaFree(exact); exact = nullptr; cap_exact = 0;
+            if ((e = cudaMalloc(&exact, cap * sizeof(RayRecord))) != cudaSuccess) return e;
+            cap_exact = cap;
+        }
+        const uint64_t want = cap / 24 + 4096;   // room for the undecided samples of a tile (capi.cu: api_get_workspace)
+        if (want > cap_queue) {
+            cudaFree(ws.queue); ws.queue = nullptr; cap_queue = 0;
+            if ((e = cudaMalloc(&ws.queue, want * sizeof(unsigned long long))) != cudaSuccess) return e;
+            cap_queue = want;
+        }
+        ws.capacity = cap_queue;
+        return cudaSuccess;
     }
 };
+
+void free_job_buffers(void* p) { delete static_cast<JobBuffers*>(p); }
 
 }  // namespace
 
@@ -192,34 +243,33 @@ extern "C" zoicb_status zoicb_run_job(zoicb_ctx* ctx, const zoicb_job* job, zoic
     if (gathered && !job->gather_counts) return api_fail(ZOICB_ERR_INVALID_ARGUMENT, "zoicb_run_job: a gathered job needs gather_counts (every rank's sample count)");
     const uint64_t rounds = gathered ? std::max<uint64_t>(ntiles, gather_rounds(g, job->gather_counts)) : ntiles;
 
-    JobBuffers B;
+    std::lock_guard<std::mutex> job_lock(ctx->job_mu);
+    if (!ctx->job_cache) { ctx->job_cache = new JobBuffers(); ctx->job_cache_free = free_job_buffers; }
+    JobBuffers& B = *static_cast<JobBuffers*>(ctx->job_cache);
+    B.begin_job();
     const int nray = gathered ? 0 : (job->serial ? 1 : 2);
     const int nsmp = job->serial ? 1 : 2;
     const uint64_t cap = std::min<uint64_t>(tile, job->count);
-    for (int i = 0; i < nsmp; ++i) ZCUDA(cudaMalloc(&B.samples[i], cap * sizeof(float4)), "cudaMalloc(job samples)");
-    for (int i = 0; i < nray; ++i) ZCUDA(cudaMalloc(&B.rays[i], cap * sizeof(RayRecord)), "cudaMalloc(job rays)");
-    if (job->census) ZCUDA(cudaMalloc(&B.exact, cap * sizeof(RayRecord)), "cudaMalloc(job census rays)");
-    B.ws.capacity = cap / 24 + 4096;   // room for the undecided samples of a tile (capi.cu: api_get_workspace)
-    ZCUDA(cudaMalloc(&B.ws.counters, 4 * sizeof(unsigned long long)), "cudaMalloc(job scratch)");
-    ZCUDA(cudaMalloc(&B.ws.queue, B.ws.capacity * sizeof(unsigned long long)), "cudaMalloc(job scratch)");
-    ZCUDA(cudaMalloc(&B.stats, 2 * sizeof(DeviceStats)), "cudaMalloc(job stats)");
-    ZCUDA(cudaMalloc(&B.consume, sizeof(ConsumeTotals)), "cudaMalloc(job totals)");
-    ZCUDA(cudaMalloc(&B.census, sizeof(CensusTotals)), "cudaMalloc(job totals)");
-    ZCUDA(cudaMemset(B.stats, 0, 2 * sizeof(DeviceStats)), "cudaMemset");
-    ZCUDA(cudaMemset(B.consume, 0, sizeof(ConsumeTotals)), "cudaMemset");
-    ZCUDA(cudaMemset(B.census, 0, sizeof(CensusTotals)), "cudaMemset");
-    ZCUDA(cudaStreamCreateWithFlags(&B.s_syn, cudaStreamNonBlocking), "cudaStreamCreate");
-    ZCUDA(cudaStreamCreateWithFlags(&B.s_gen, cudaStreamNonBlocking), "cudaStreamCreate");
-    ZCUDA(cudaStreamCreateWithFlags(&B.s_con, cudaStreamNonBlocking), "cudaStreamCreate");
-    if (job->serial) { cudaStreamDestroy(B.s_syn); cudaStreamDestroy(B.s_con); B.s_syn = B.s_con = nullptr; }
+    {
+        const cudaError_t ea = B.ensure(cap, nsmp, nray, job->census != 0);
+        if (ea != cudaSuccess) {   // drop the cache: a later, smaller job may still fit
+            cudaGetLastError();
+            delete &B;
+            ctx->job_cache = nullptr;
+            return api_cuda_fail(ea, "zoicb_run_job: device memory for the tile buffers");
+        }
+    }
+    ZCUDA(cudaMemsetAsync(B.stats, 0, 2 * sizeof(DeviceStats), B.s_gen), "cudaMemset");
+    ZCUDA(cudaMemsetAsync(B.consume, 0, sizeof(ConsumeTotals), B.s_gen), "cudaMemset");
+    ZCUDA(cudaMemsetAsync(B.census, 0, sizeof(CensusTotals), B.s_gen), "cudaMemset");
     cudaStream_t s_syn = job->serial ? B.s_gen : B.s_syn, s_gen = B.s_gen, s_con = job->serial ? B.s_gen : B.s_con;
 
     // events: synthesised[slot], generated[slot], consumed[slot] (a slot is reused two tiles later)
     cudaEvent_t ev_syn[2] = {B.event(), B.event()}, ev_gen[3] = {B.event(), B.event(), B.event()};
     cudaEvent_t ev_con[3] = {B.event(), B.event(), B.event()}, ev_used[2] = {B.event(), B.event()};
-    cudaEvent_t t0 = B.event(cudaEventDefault), t1 = B.event(cudaEventDefault);
+    cudaEvent_t t0 = B.event(true), t1 = B.event(true);
     std::vector<cudaEvent_t> g0(ntiles), g1(ntiles);   // around the generate kernels of every tile, on their stream
-    for (uint64_t k = 0; k < ntiles; ++k) { g0[k] = B.event(cudaEventDefault); g1[k] = B.event(cudaEventDefault); }
+    for (uint64_t k = 0; k < ntiles; ++k) { g0[k] = B.event(true); g1[k] = B.event(true); }
     double gen_ms = 0.0;
     int launches = 0;
     cudaError_t e = cudaSuccess;

@@ -522,8 +522,8 @@ cudaError_t launch_generate(const CameraState& cam, int mode, const float4* samp
     const bool image = cam.use_image != 0;
     size_t smem = 0;
     int stage = 0;
-    if (image) {  // row tables staged in shared memory; zoicb_create rejects images with more than kMaxBokehRows rows
-        smem = (size_t)cam.bokeh.h * 8;
+    if (image) {  // row-indexed tables staged in shared memory (kernel_common.cuh); zoicb_create rejects images with more than kMaxBokehRows rows
+        smem = bokeh_smem_bytes(cam.bokeh.w, cam.bokeh.h, cam.bokeh.row_shift);
         stage = 1;
     }
 #define ZL(M, I, U) launch_variant<M, I, U>(cam, mode, samples, n, first_index, seed, rays, stats, st, ws, smem, stage, launches)
@@ -548,7 +548,7 @@ cudaError_t launch_draw_paths(const CameraState& cam, const float4* samples, uin
     if (n == 0) return cudaSuccess;
     const unsigned grid = (n + 127) / 128;
     const bool image = cam.use_image != 0, lut = cam.lens.use_lut != 0;
-    const size_t rows_smem = image ? (size_t)cam.bokeh.h * 8 : 0;
+    const size_t rows_smem = image ? bokeh_smem_bytes(cam.bokeh.w, cam.bokeh.h, cam.bokeh.row_shift) : 0;
 #define ZD(I, U) draw_paths_kernel<I, U><<<grid, 128, rows_smem, st>>>(cam, samples, n, indices, first_index, seed, quads, kinds, counts, cap)
     if (image) { if (lut) ZD(true, true); else ZD(true, false); }
     else { if (lut) ZD(false, true); else ZD(false, false); }

@@ -40,6 +40,9 @@ cudaError_t launch_bokeh_build(const float* d_rgb, int w, int h, int nch, float*
                                float* d_total, float* d_row_mass, float* d_cdf_row, int32_t* d_row_idx,
                                float* d_cdf_col, uint16_t* d_rel_col, int row_shift, int col_shift, uint16_t* d_row_guide,
                                uint16_t* d_col_guide, cudaStream_t st, int* launches);
+// ray differentials (differentials.cu): out = n x 12 floats (dOdx, dOdy, dDdx, dDdy)
+cudaError_t launch_differentials(const CameraState& cam, const float4* samples, uint64_t n, uint64_t first_index, uint64_t seed,
+                                 float dsx, float dsy, const RayRecord* rays, float4* out, cudaStream_t st, int* launches);
 cudaError_t measure_fp32_peak(double* tflops, int* launches);
 
 }  // namespace zoicb
