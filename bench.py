@@ -247,6 +247,26 @@ def pcie_yardstick(torch, dev, barrier, reduce_max, mb=256, reps=6):
     return out
 
 
+def bind_to_gpu_numa_node(index):
+    """Pins this process to the CPU cores NVML reports as local to GPU `index`, BEFORE any pinned host buffer is allocated:
+    pinned pages are placed on the NUMA node of the allocating thread, so every rank's staging memory and copy-issuing
+    thread end up next to its own GPU's PCIe root instead of all on node 0.  Returns the core list, or None."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = [64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1]
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return allowed
+    except Exception:
+        pass
+    return None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -259,6 +279,7 @@ def main():
     ap.add_argument("--spp", type=int, default=0, help="override samples per pixel (profiling: a small job that still covers the whole film)")
     ap.add_argument("--stream", action="store_true", help="stream the job through zoicb_run_job even if it would fit in HBM")
     ap.add_argument("--tile-log2", type=int, default=27, help="streamed jobs: samples per tile")
+    ap.add_argument("--serial", action="store_true", help="streamed jobs: one stream, no overlap of synthesis / generation / consumption (A/B)")
     ap.add_argument("--e2e-samples", type=int, default=1 << 27)
     ap.add_argument("--cpu-samples", type=int, default=1 << 25, help="CPU baseline sample size (all cores)")
     ap.add_argument("--census-rays", type=int, default=2_123_366_400, help="N = 1: rays of the GUARDED-vs-EXACT census (0 = off)")
@@ -291,6 +312,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
+    affinity = bind_to_gpu_numa_node(local) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
@@ -347,7 +369,7 @@ def main():
         if resident:
             cam.create_rays(samples, seed=wl.seed, first_index=first, out=rays)
         else:
-            job_results.append(cam.run_job(W, H, spp_pp, sseed, wl.seed, first, n, tile=tile))
+            job_results.append(cam.run_job(W, H, spp_pp, sseed, wl.seed, first, n, tile=tile, serial=args.serial))
 
     for _ in range(args.warmup):
         step()
@@ -456,7 +478,8 @@ def main():
             per_rank_d2h = 32.0 * m / dt / 1e9
             e2e["pcie"] = y
             e2e["d2h_gbs_per_rank"] = per_rank_d2h
-            e2e["pcie_frac"] = per_rank_d2h / y["h2d_d2h_concurrent_each"]
+            # the download (32 B/ray) is the binding direction; the upload (16 B/ray) shares the link at half its rate
+            e2e["pcie_frac"] = per_rank_d2h / y["d2h_alone"]
         except Exception as exc:   # a yardstick, not the measurement
             e2e["pcie"] = {"error": repr(exc)}
 
@@ -545,7 +568,7 @@ def main():
                "sharding": "strong: rank r owns samples [r N/G, (r+1) N/G) of the one %dx%dx%d job (%s split); no data-path "
                            "collective in `value`" % (wl.W, wl.H, wl.spp, split),
                "wall_ms_per_step": reduce_max(wall_ms) / args.steps if world == 1 else None,
-               "create": create_times}
+               "create": create_times, "cpu_affinity": ("%d cores local to the GPU: %d-%d" % (len(affinity), affinity[0], affinity[-1])) if affinity else None}
         if checksum is not None:
             run["checksum"] = checksum
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,

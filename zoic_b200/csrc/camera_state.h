@@ -10,7 +10,7 @@ namespace zoicb {
 
 constexpr int kMaxElements = 24;
 constexpr int kLutSize = 32;
-constexpr int kMaxBokehRows = 5120;  // 16 bytes per row (+ row guide, + dx for images up to 4096 wide) are staged in shared memory
+constexpr int kMaxBokehRows = 5120;  // row CDF + row indices are staged in 40 KB of shared memory
 // Guide ("cutpoint") tables of the inverse-CDF searches have G + 2 entries with G = 2^shift cells (see BokehTables).
 // Default resolution: the smallest power of two that is >= the table length, within [2^4, 2^16].
 inline int default_guide_shift(int n) {
@@ -93,7 +93,6 @@ struct BokehTables {
     // dx_of_col[c] = fl(fl(fl(c - (h-1)/2) / fl(w)) * 2), dy_of_row[r] = fl(fl(-fl(r - (w-1)/2) / fl(h)) * 2)
     const float* dx_of_col;      // [w]
     const float* dy_of_row;      // [h]
-    const float* col_final;      // [h]: cdf_column[row * w + w - 1], the final value of the row's column CDF
     int32_t w, h;
     int32_t row_shift, col_shift;   // log2 of the guide resolutions
 };

@@ -118,10 +118,9 @@ bool bokeh_build_gpu(void* user, const float* rgb, int w, int h, int nch, HostBo
         if (cudaMemcpy(out->row_guide.data(), c->d_row_guide, ng_row * sizeof(uint16_t), cudaMemcpyDeviceToHost) != cudaSuccess) break;
         if (cudaMemcpy(out->col_guide.data(), c->d_col_guide, ng_col * sizeof(uint16_t), cudaMemcpyDeviceToHost) != cudaSuccess) break;
         {   // lens coordinates per column / per row, with the reference's operations (src/zoic.cpp:441,466,479-484)
-            std::vector<float> dxy((size_t)w + 2 * (size_t)h);   // dx_of_col[w], dy_of_row[h], col_final[h]
+            std::vector<float> dxy((size_t)w + h);
             for (int col = 0; col < w; ++col) dxy[col] = xmul(xdiv((float)(col - (h - 1) / 2), (float)w), 2.0f);
             for (int row = 0; row < h; ++row) dxy[(size_t)w + row] = xmul(xdiv(xmul((float)(row - (w - 1) / 2), -1.0f), (float)h), 2.0f);
-            for (int row = 0; row < h; ++row) dxy[(size_t)w + h + row] = out->cdf_column[(size_t)row * w + (w - 1)];
             if (cudaMalloc(&c->d_dxy, dxy.size() * sizeof(float)) != cudaSuccess) break;
             if (cudaMemcpy(c->d_dxy, dxy.data(), dxy.size() * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) break;
         }
@@ -233,14 +232,14 @@ zoicb_status zoicb_create(const zoicb_params* params, const float* rgb, int widt
     if (hb.valid()) {   // tables were built on the device by bokeh_build_gpu and stayed there
         bt.cdf_row = c->d_cdf_row; bt.row_indices = c->d_row_idx; bt.cdf_column = c->d_cdf_col; bt.rel_column = c->d_rel_col;
         bt.row_guide = c->d_row_guide; bt.col_guide = c->d_col_guide;
-        bt.dx_of_col = c->d_dxy; bt.dy_of_row = c->d_dxy + hb.w; bt.col_final = c->d_dxy + hb.w + hb.h;
+        bt.dx_of_col = c->d_dxy; bt.dy_of_row = c->d_dxy + hb.w;
         bt.w = hb.w; bt.h = hb.h; bt.row_shift = hb.row_shift; bt.col_shift = hb.col_shift;
     } else if (hb.degenerate) {
         // An image the reference accepts but treats as invalid (fewer than 3 channels, src/zoic.cpp:135-137): every
         // bokehSample answers the lens centre (0, 0) (:420-425).  The kernels keep their one code path: a 1 x 1 table whose
         // CDF entry is +inf (every u, NaN included after the clamp, lands on entry 0) and whose lens coordinates are +0.
         const float inf = std::numeric_limits<float>::infinity();
-        const float cdf1[1] = {inf}, zero2[3] = {0.0f, 0.0f, inf};   // dx, dy, final value of the column CDF
+        const float cdf1[1] = {inf}, zero2[2] = {0.0f, 0.0f};
         const int32_t idx1[1] = {0};
         const uint16_t rel1[1] = {0}, guide3[3] = {0, 0, 0};   // shift 0: G = 1 cell, G + 2 = 3 entries
         if ((e = cudaMalloc(&c->d_cdf_row, sizeof cdf1)) != cudaSuccess) return bail(e, "cudaMalloc(bokeh)");
@@ -259,7 +258,7 @@ zoicb_status zoicb_create(const zoicb_params* params, const float* rgb, int widt
         if ((e = cudaMemcpy(c->d_dxy, zero2, sizeof zero2, cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e, "cudaMemcpy(bokeh)");
         bt.cdf_row = c->d_cdf_row; bt.row_indices = c->d_row_idx; bt.cdf_column = c->d_cdf_col; bt.rel_column = c->d_rel_col;
         bt.row_guide = c->d_row_guide; bt.col_guide = c->d_col_guide;
-        bt.dx_of_col = c->d_dxy; bt.dy_of_row = c->d_dxy + 1; bt.col_final = c->d_dxy + 2;
+        bt.dx_of_col = c->d_dxy; bt.dy_of_row = c->d_dxy + 1;
         bt.w = 1; bt.h = 1; bt.row_shift = 0; bt.col_shift = 0;
     }
     if ((e = cudaDeviceSynchronize()) != cudaSuccess) return bail(e, "zoicb_create");

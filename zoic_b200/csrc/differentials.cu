@@ -97,7 +97,7 @@ cudaError_t launch_differentials(const CameraState& cam, const float4* samples, 
                                  float dsx, float dsy, const RayRecord* rays, float4* out, cudaStream_t st, int* launches) {
     if (n == 0) return cudaSuccess;
     const bool image = cam.use_image != 0, lut = cam.lens.use_lut != 0;
-    const size_t smem = image ? bokeh_smem_bytes(cam.bokeh.w, cam.bokeh.h, cam.bokeh.row_shift) : 0;
+    const size_t smem = image ? bokeh_smem_bytes(cam.bokeh.h) : 0;
     const uint64_t want = (n + 255) / 256, cap = (uint64_t)sm_count() * 4;
     const unsigned grid = (unsigned)(want < cap ? want : cap);
 #define ZD(M, I, U) differentials_kernel<M, I, U><<<grid, 256, smem, st>>>(cam, samples, n, first_index, seed, dsx, dsy, rays, out)

@@ -146,6 +146,7 @@ struct zoicb_gather {
     std::vector<cudaEvent_t> ev_eaten;                // consumer: slot consumed
     std::vector<uint64_t> counts;
     uint64_t base = 0, job_base = 0, job_rounds = 0;   // rounds of all earlier jobs; of the current / last job
+    bool serial = false;                    // current job: ship / wait / consume on the caller's stream (no overlap; A/B)
     NcclComm comm = nullptr;
     bool own_comm = false;
     unsigned long long timeout_ns = 10ull * 1000 * 1000 * 1000;   // ZOICB_GATHER_TIMEOUT_S overrides
@@ -172,9 +173,10 @@ uint64_t gather_rounds(const zoicb_gather* g, const uint64_t* counts) {
     return r;
 }
 
-cudaError_t gather_begin(zoicb_gather* g, const uint64_t* counts, cudaStream_t st) {
+cudaError_t gather_begin(zoicb_gather* g, const uint64_t* counts, cudaStream_t st, bool serial) {
     (void)st;
     if (!g->connected) return cudaErrorNotReady;
+    g->serial = serial;
     g->counts.assign(counts, counts + g->world);
     g->job_base = g->base;
     g->job_rounds = gather_rounds(g, counts);
@@ -211,6 +213,7 @@ cudaError_t gather_commit(zoicb_gather* g, uint64_t round, uint64_t m, cudaStrea
     cudaError_t e;
     NcclApi& N = nccl();
     const uint64_t G = g->global_round(round);
+    cudaStream_t sc = g->serial ? st : g->s_copy;   // the stream that ships (producer) or waits and consumes (consumer)
     if (!g->is_consumer()) {
         Flags* cf = g->peer_flags[g->consumer];
         if (g->transport == ZOICB_GATHER_FUSED) {
@@ -219,36 +222,36 @@ cudaError_t gather_commit(zoicb_gather* g, uint64_t round, uint64_t m, cudaStrea
             return cudaGetLastError();
         }
         if ((e = cudaEventRecord(g->ev_gen, st)) != cudaSuccess) return e;
-        if ((e = cudaStreamWaitEvent(g->s_copy, g->ev_gen, 0)) != cudaSuccess) return e;
+        if ((e = cudaStreamWaitEvent(sc, g->ev_gen, 0)) != cudaSuccess) return e;
         if (g->transport == ZOICB_GATHER_PUSH) {
             if (G >= (uint64_t)g->slots) {
-                wait_kernel<<<1, 32, 0, g->s_copy>>>(&g->flags->freed, 1, -1, G - g->slots + 1, &g->flags->error, g->timeout_ns);
+                wait_kernel<<<1, 32, 0, sc>>>(&g->flags->freed, 1, -1, G - g->slots + 1, &g->flags->error, g->timeout_ns);
                 if (launches) *launches += 1;
                 if ((e = cudaGetLastError()) != cudaSuccess) return e;
             }
             if (m && (e = cudaMemcpyAsync(g->slot_base(g->peer_data, round, g->rank), g->stage[round & 1], m * sizeof(RayRecord),
-                                          cudaMemcpyDefault, g->s_copy)) != cudaSuccess) return e;
-            signal_kernel<<<1, 1, 0, g->s_copy>>>(&cf->arrive[g->rank], G + 1);
+                                          cudaMemcpyDefault, sc)) != cudaSuccess) return e;
+            signal_kernel<<<1, 1, 0, sc>>>(&cf->arrive[g->rank], G + 1);
             if (launches) *launches += 1;
             if ((e = cudaGetLastError()) != cudaSuccess) return e;
         } else {   // NCCL: the rendezvous with the consumer's receive is the back-pressure
-            if (m && N.Send(g->stage[round & 1], m * sizeof(RayRecord), kNcclInt8, g->consumer, g->comm, g->s_copy) != 0) return cudaErrorUnknown;
+            if (m && N.Send(g->stage[round & 1], m * sizeof(RayRecord), kNcclInt8, g->consumer, g->comm, sc) != 0) return cudaErrorUnknown;
         }
-        return cudaEventRecord(g->ev_done[round & 1], g->s_copy);
+        return cudaEventRecord(g->ev_done[round & 1], sc);
     }
     // ---- consumer: everything below runs on its own stream, behind this round's own share
     if ((e = cudaEventRecord(g->ev_gen, st)) != cudaSuccess) return e;
-    if ((e = cudaStreamWaitEvent(g->s_copy, g->ev_gen, 0)) != cudaSuccess) return e;
+    if ((e = cudaStreamWaitEvent(sc, g->ev_gen, 0)) != cudaSuccess) return e;
     if (g->transport == ZOICB_GATHER_NCCL) {
         if (N.GroupStart() != 0) return cudaErrorUnknown;
         for (int r = 0; r < g->world; ++r) {
             const uint64_t mr = g->count_of(r, round);
             if (r == g->rank || !mr) continue;
-            if (N.Recv(g->slot_base(g->data, round, r), mr * sizeof(RayRecord), kNcclInt8, r, g->comm, g->s_copy) != 0) { N.GroupEnd(); return cudaErrorUnknown; }
+            if (N.Recv(g->slot_base(g->data, round, r), mr * sizeof(RayRecord), kNcclInt8, r, g->comm, sc) != 0) { N.GroupEnd(); return cudaErrorUnknown; }
         }
         if (N.GroupEnd() != 0) return cudaErrorUnknown;
     } else {
-        wait_kernel<<<1, 64, 0, g->s_copy>>>(g->flags->arrive, g->world, g->rank, G + 1, &g->flags->error, g->timeout_ns);
+        wait_kernel<<<1, 64, 0, sc>>>(g->flags->arrive, g->world, g->rank, G + 1, &g->flags->error, g->timeout_ns);
         if (launches) *launches += 1;
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
     }
@@ -256,22 +259,23 @@ cudaError_t gather_commit(zoicb_gather* g, uint64_t round, uint64_t m, cudaStrea
     bool full = true;
     for (int r = 0; r < g->world; ++r) full = full && g->count_of(r, round) == g->tile;
     if (full) {
-        if ((e = launch_consume(g->slot_base(g->data, round, 0), (uint64_t)g->world * g->tile, d_totals, g->s_copy, launches)) != cudaSuccess) return e;
+        if ((e = launch_consume(g->slot_base(g->data, round, 0), (uint64_t)g->world * g->tile, d_totals, sc, launches)) != cudaSuccess) return e;
     } else {
         for (int r = 0; r < g->world; ++r)
-            if ((e = launch_consume(g->slot_base(g->data, round, r), g->count_of(r, round), d_totals, g->s_copy, launches)) != cudaSuccess) return e;
+            if ((e = launch_consume(g->slot_base(g->data, round, r), g->count_of(r, round), d_totals, sc, launches)) != cudaSuccess) return e;
     }
     if (g->transport != ZOICB_GATHER_NCCL) {
         PeerFlags pf;
         for (int r = 0; r < g->world; ++r) pf.freed[r] = g->peer_flags[r] ? &g->peer_flags[r]->freed : nullptr;
-        release_kernel<<<1, 64, 0, g->s_copy>>>(pf, g->world, g->rank, G + 1);
+        release_kernel<<<1, 64, 0, sc>>>(pf, g->world, g->rank, G + 1);
         if (launches) *launches += 1;
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
     }
-    return cudaEventRecord(g->ev_eaten[G % g->slots], g->s_copy);
+    return cudaEventRecord(g->ev_eaten[G % g->slots], sc);
 }
 
 cudaError_t gather_end(zoicb_gather* g, cudaStream_t st) {
+    if (g->serial) return cudaSuccess;
     cudaError_t e = cudaEventRecord(g->ev_gen, g->s_copy);
     if (e != cudaSuccess) return e;
     return cudaStreamWaitEvent(st, g->ev_gen, 0);

@@ -12,8 +12,9 @@ int gather_device(const zoicb_gather* g);
 uint64_t gather_tile_rays(const zoicb_gather* g);   // records every rank contributes per round (at most)
 // number of rounds all ranks run for these per-rank totals (counts[world], the same array on every rank)
 uint64_t gather_rounds(const zoicb_gather* g, const uint64_t* counts);
-// starts a job: remembers the per-rank totals, resets the round counters; `st` is the stream the caller generates on
-cudaError_t gather_begin(zoicb_gather* g, const uint64_t* counts, cudaStream_t st);
+// starts a job: remembers the per-rank totals and numbers its rounds; `st` is the stream the caller generates on;
+// serial: shipping, waiting and consuming happen on `st` itself instead of the gather's own stream (no overlap)
+cudaError_t gather_begin(zoicb_gather* g, const uint64_t* counts, cudaStream_t st, bool serial);
 // where this rank's generate kernels write their records of `round`; `st` waits until that memory may be overwritten
 cudaError_t gather_acquire(zoicb_gather* g, uint64_t round, cudaStream_t st, RayRecord** dst);
 // this rank's m records of `round` are complete in stream order on `st`: ship / signal them; on the consumer rank also

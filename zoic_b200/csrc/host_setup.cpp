@@ -502,7 +502,7 @@ zoicb_status build_camera(const zoicb_params& p, const float* rgb, int w, int h,
             return (m >= 1 && m <= 16) ? m : default_guide_shift(n);
         };
         out->bokeh.row_shift = shift_from_env("ZOICB_GUIDE_ROW_LOG2", h);
-        out->bokeh.col_shift = shift_from_env("ZOICB_GUIDE_COL_LOG2", w);
+        out->bokeh.col_shift = shift_from_env("ZOICB_GUIDE_COL_LOG2", 2 * w);   // two cells per column: +1 % over one (profiles/r02_ab.txt)
         if (nch < 3) {
             // imageData::isValid() is false for fewer than 3 channels (src/zoic.cpp:135-137): the reference builds no
             // tables and every bokehSample answers (0, 0) (:420-425).  Kept: the device gets a 1 x 1 stand-in (capi.cu).

@@ -11,6 +11,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -32,11 +33,12 @@ __global__ void __launch_bounds__(256)
 consume_rays_kernel(const RayRecord* __restrict__ rays, uint64_t n, ConsumeTotals* __restrict__ out) {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     unsigned long long sum = 0, zero = 0, tries = 0, cnt = 0;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        unsigned w[8];
+    auto load = [&](uint64_t i, unsigned* w) {
         asm volatile("ld.global.cs.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                      : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7])
                      : "l"(rays + i));
+    };
+    auto eat = [&](const unsigned* w) {
         sum += (unsigned long long)w[0] * 0x9E3779B1u + (unsigned long long)w[1] * 0x85EBCA77u +
                (unsigned long long)w[2] * 0xC2B2AE3Du + (unsigned long long)w[3] * 0x27D4EB2Fu +
                (unsigned long long)w[4] * 0x165667B1u + (unsigned long long)w[5] * 0xD3A2646Du +
@@ -44,6 +46,19 @@ consume_rays_kernel(const RayRecord* __restrict__ rays, uint64_t n, ConsumeTotal
         zero += (__uint_as_float(w[3]) == 0.0f) ? 1u : 0u;
         tries += (unsigned long long)__uint_as_float(w[7]);
         cnt += 1;
+    };
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + stride < n; i += 2 * stride) {   // two records in flight per thread
+        unsigned a[8], b[8];
+        load(i, a);
+        load(i + stride, b);
+        eat(a);
+        eat(b);
+    }
+    if (i < n) {
+        unsigned a[8];
+        load(i, a);
+        eat(a);
     }
     __shared__ unsigned long long acc[4];
     if (threadIdx.x < 4) acc[threadIdx.x] = 0ull;
@@ -131,6 +146,8 @@ static unsigned stream_grid(uint64_t n, int ctas_per_sm) {
 
 cudaError_t launch_consume(const RayRecord* rays, uint64_t n, void* d_totals, cudaStream_t st, int* launches) {
     if (n == 0) return cudaSuccess;
+    static const bool skip = [] { const char* v = getenv("ZOICB_JOB_NO_CONSUME"); return v && atoi(v) != 0; }();   // diagnosis only
+    if (skip) return cudaSuccess;
     // 2 CTAs per SM: the consumer runs NEXT to the persistent generate kernel of the following tile, in the registers
     // and warp slots that kernel leaves free
     consume_rays_kernel<<<stream_grid(n, 2), 256, 0, st>>>(rays, n, static_cast<ConsumeTotals*>(d_totals));
@@ -275,7 +292,7 @@ extern "C" zoicb_status zoicb_run_job(zoicb_ctx* ctx, const zoicb_job* job, zoic
     cudaError_t e = cudaSuccess;
     const char* what = "";
 
-    if (gathered && (e = gather_begin(g, job->gather_counts, s_gen)) != cudaSuccess) return api_cuda_fail(e, "zoicb_run_job: gather begin");
+    if (gathered && (e = gather_begin(g, job->gather_counts, s_gen, job->serial != 0)) != cudaSuccess) return api_cuda_fail(e, "zoicb_run_job: gather begin");
     ZCUDA(cudaEventRecord(t0, s_gen), "cudaEventRecord");
     if (!job->serial) {
         ZCUDA(cudaStreamWaitEvent(s_syn, t0, 0), "cudaStreamWaitEvent");

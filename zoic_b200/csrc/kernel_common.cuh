@@ -37,15 +37,12 @@ __device__ __forceinline__ void store_ray(RayRecord* __restrict__ rays, uint64_t
 // bracket ever spans the flat tail.
 // Brackets of up to ZOICB_BOKEH_COUNT entries (warp maximum) are resolved by COUNTING the entries that are not greater
 // than u: independent, predicated loads (a lane only loads the entries of its own bracket) instead of a chain of
-// dependent probes; the payload of the answer entry (`pay(i)`: the column search's pixel index) is fetched by the same
-// loads, so nothing depends on the count.  Longer brackets (photograph-like images whose CDF is nearly flat towards
-// 1), NaN and negative u (whole range) take the libstdc++ first/len halving with a warp-uniform number of rounds and
-// predicated updates: no lane leaves the loop early.  (With a data-dependent trip count ptxas 12.9 let the early lanes
-// run ahead and re-use the uniform registers that hold the table pointers while the late lanes were still reading them.)
-// Returns min(answer, n - 1) -- what both callers clamp to (:437, :462) -- and its payload.
-template <typename Load, typename Guide, typename Pay>
-__device__ __forceinline__ int upper_bound_guided(int n, int shift, float u, float final_value, Load load, Guide guide, Pay pay,
-                                                  int* payload) {
+// dependent probes.  Longer brackets (photograph-like images whose CDF is nearly flat towards 1), NaN and negative u
+// (whole range) take the libstdc++ first/len halving with a warp-uniform number of rounds and predicated updates: no
+// lane leaves the loop early.  (With a data-dependent trip count ptxas 12.9 let the early lanes run ahead and re-use the
+// uniform registers that hold the table pointers while the late lanes were still reading them.)
+template <typename Load, typename Guide>
+__device__ __forceinline__ int upper_bound_guided(int n, int shift, float u, Load load, Guide guide) {
     int first = 0, len = n;
     bool past = false;
     if (u >= 0.0f) {
@@ -54,31 +51,18 @@ __device__ __forceinline__ int upper_bound_guided(int n, int shift, float u, flo
         const int k = f >= (float)G ? G : (int)f;
         first = guide(k);
         len = guide(k + 1) - first;
-        past = u >= final_value;   // false for a NaN table (black image): its guides all hold n
+        past = u >= load(n - 1);   // false for a NaN table (black image): its guides all hold n
     }
     const int maxlen = (int)__reduce_max_sync(__activemask(), (unsigned)len);
     constexpr int kCount = ZOICB_BOKEH_COUNT;
     if (kCount > 0 && maxlen <= kCount) {
-        // candidates first .. first + len: entry j < len is passed over when it is not greater than u; the first entry that
-        // is not passed over (j == len at the latest) is the answer
-        int cnt = 0, got = 0;
-        bool found = false;
-        if (past) { first = n - 1; len = 0; }   // u >= final: the answer n clamps to the last entry
+        int cnt = 0;
 #pragma unroll
-        for (int j = 0; j <= kCount; ++j) {
-            if (j > maxlen) break;   // warp-uniform
-            if (j <= len) {
-                const int i = first + j < n ? first + j : n - 1;
-                const float v = load(i);
-                const int q = pay(i);
-                const bool over = j < len && !(u < v);
-                cnt += over ? 1 : 0;
-                if (!over && !found) { got = q; found = true; }
-            }
+        for (int j = 0; j < kCount; ++j) {
+            if (j >= maxlen) break;   // warp-uniform
+            if (j < len) cnt += (u < load(first + j)) ? 0 : 1;
         }
-        *payload = got;
-        const int c = first + cnt;
-        return c < n ? c : n - 1;
+        return past ? n : first + cnt;
     }
     const int rounds = 32 - __clz(maxlen);
     for (int it = 0; it < rounds; ++it) {
@@ -90,52 +74,41 @@ __device__ __forceinline__ int upper_bound_guided(int n, int shift, float u, flo
         first = (live && !left) ? mid + 1 : first;
         len = live ? (left ? half : len - half - 1) : 0;
     }
-    int c = past ? n : first;
-    if (c >= n) c = n - 1;
-    *payload = pay(c);
-    return c;
+    return past ? n : first;
 }
 
-// Dynamic shared memory of every kernel that samples an image-shaped aperture: the tables that are indexed by ROW (row
-// CDF, row indices, final value of every row's column CDF, dy of the row), the row guide table and -- for images up to
-// kMaxStagedCols wide -- dx of the column; the per-pixel column tables (CDF, pixel index, column guide) stay in global
-// memory (L1 / L2 resident).  Addressed as shared memory (no generic pointers).
+// The row tables (cdfRow, rowIndices: 8 bytes per image row) are always staged in dynamic shared memory --
+// s_rows[0..h) holds the CDF, s_rows[h..2h) the row indices -- and addressed as shared memory (no generic
+// pointers); the per-row column tables stay in global memory (L1/L2 resident).
 extern __shared__ float s_rows[];
-constexpr int kMaxStagedCols = 4096;
 
-__host__ __device__ inline unsigned bokeh_smem_bytes(int w, int h, int row_shift) {
-    const unsigned floats = 4u * (unsigned)h + (w <= kMaxStagedCols ? (unsigned)w : 0u);
-    const unsigned guide = (((1u << row_shift) + 2u) * 2u + 3u) & ~3u;
-    return (floats * 4u + guide + 15u) & ~15u;
-}
+__host__ __device__ inline unsigned bokeh_smem_bytes(int h) { return ((unsigned)h * 8u + 15u) & ~15u; }
 
 struct BokehView {
     const float* cdf_col;     // global
     const uint16_t* rel_col;
+    const uint16_t* row_guide;
     const uint16_t* col_guide;
-    const float* dx_of_col;   // global copy (wide images)
-    const float* s_final;     // shared: final value of the row's column CDF, by actual row
-    const float* s_dy;        // shared
-    const float* s_dx;        // shared, or null
-    const uint16_t* s_row_guide;   // shared
+    const float* dx_of_col;
+    const float* dy_of_row;
     int w, h;
     int row_shift, col_shift;
 };
 
 __device__ __forceinline__ void bokeh_sample(const BokehView& b, float u_row, float u_col, float* dx, float* dy) {
-    int row;
-    upper_bound_guided(b.h, b.row_shift, u_row, s_rows[b.h - 1], [&](int i) { return s_rows[i]; },
-                       [&](int k) { return (int)b.s_row_guide[k]; }, [&](int i) { return __float_as_int(s_rows[b.h + i]); }, &row);
-    const int start = row * b.w;   // the reference centres the row with the WIDTH (:441) and the column with the HEIGHT (:466):
-                                   // both folded into the dx / dy tables (camera_state.h)
+    int r = upper_bound_guided(b.h, b.row_shift, u_row, [&](int i) { return s_rows[i]; }, [&](int k) { return (int)__ldg(b.row_guide + k); });
+    if (r >= b.h) r = b.h - 1;
+    const int row = __float_as_int(s_rows[b.h + r]);
+    const int start = row * b.w;
     const float* __restrict__ col = b.cdf_col + start;
-    const uint16_t* __restrict__ rc = b.rel_col + start;
     const uint16_t* __restrict__ cg = b.col_guide + row * ((1 << b.col_shift) + 2);
-    int rel;
-    upper_bound_guided(b.w, b.col_shift, u_col, b.s_final[row], [&](int i) { return __ldg(col + i); },
-                       [&](int k) { return (int)__ldg(cg + k); }, [&](int i) { return (int)__ldg(rc + i); }, &rel);
-    *dx = b.s_dx ? b.s_dx[rel] : __ldg(b.dx_of_col + rel);
-    *dy = b.s_dy[row];
+    int c = upper_bound_guided(b.w, b.col_shift, u_col, [&](int i) { return __ldg(col + i); }, [&](int k) { return (int)__ldg(cg + k); });
+    if (c >= b.w) c = b.w - 1;
+    const int rel = (int)__ldg(b.rel_col + start + c);
+    // the reference centres the row with the WIDTH (:441) and the column with the HEIGHT (:466) and divides (:479-484):
+    // both divisions depend on the column / the row only and are tabulated once per camera with the same operations
+    *dx = __ldg(b.dx_of_col + rel);
+    *dy = __ldg(b.dy_of_row + row);
 }
 
 template <bool kImage>
@@ -155,28 +128,18 @@ __device__ __forceinline__ void draw_pair(Xor128& rng, float* first_param, float
 
 __device__ __forceinline__ BokehView stage_bokeh(const CameraState& cam) {
     BokehView b;
-    const BokehTables& t = cam.bokeh;
-    b.w = t.w; b.h = t.h;
-    b.cdf_col = t.cdf_column;
-    b.rel_col = t.rel_column;
-    b.col_guide = t.col_guide;
-    b.dx_of_col = t.dx_of_col;
-    b.row_shift = t.row_shift; b.col_shift = t.col_shift;
-    const int h = t.h, w = t.w;
-    const bool stage_dx = w <= kMaxStagedCols;
-    float* s_final = s_rows + 2 * h;
-    float* s_dy = s_rows + 3 * h;
-    float* s_dx = s_rows + 4 * h;
-    uint16_t* s_guide = reinterpret_cast<uint16_t*>(s_rows + 4 * h + (stage_dx ? w : 0));
-    for (int i = threadIdx.x; i < h; i += blockDim.x) {
-        s_rows[i] = t.cdf_row[i];
-        s_rows[h + i] = __int_as_float(t.row_indices[i]);
-        s_final[i] = t.col_final[i];
-        s_dy[i] = t.dy_of_row[i];
+    b.w = cam.bokeh.w; b.h = cam.bokeh.h;
+    b.cdf_col = cam.bokeh.cdf_column;
+    b.rel_col = cam.bokeh.rel_column;
+    b.row_guide = cam.bokeh.row_guide;
+    b.col_guide = cam.bokeh.col_guide;
+    b.dx_of_col = cam.bokeh.dx_of_col;
+    b.dy_of_row = cam.bokeh.dy_of_row;
+    b.row_shift = cam.bokeh.row_shift; b.col_shift = cam.bokeh.col_shift;
+    for (int i = threadIdx.x; i < b.h; i += blockDim.x) {
+        s_rows[i] = cam.bokeh.cdf_row[i];
+        s_rows[b.h + i] = __int_as_float(cam.bokeh.row_indices[i]);
     }
-    if (stage_dx) for (int i = threadIdx.x; i < w; i += blockDim.x) s_dx[i] = t.dx_of_col[i];
-    for (int i = threadIdx.x; i < (1 << t.row_shift) + 2; i += blockDim.x) s_guide[i] = t.row_guide[i];
-    b.s_final = s_final; b.s_dy = s_dy; b.s_dx = stage_dx ? s_dx : nullptr; b.s_row_guide = s_guide;
     __syncthreads();
     return b;
 }

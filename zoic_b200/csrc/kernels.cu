@@ -220,17 +220,29 @@ thin_persistent_kernel(const __grid_constant__ CameraState cam, const float4* __
 // ------------------------------------------------------------------------------------------------
 // synthetic samples
 // ------------------------------------------------------------------------------------------------
+// The pixel of sample i is (i / spp) mod (W H): three 64-bit divisions per sample made this kernel compute-bound (0.82 ms
+// per 2^27 samples, 2.6 TB/s of stores).  A thread walks its samples with a fixed stride, so it divides ONCE and then
+// carries (sample-in-pixel, px, py) forward with 32-bit adds: stride = (a1 W H' ... ) decomposed on entry.
 __global__ void __launch_bounds__(256)
 synth_samples_kernel(uint32_t W, uint32_t H, uint32_t spp, uint64_t seed, uint64_t first_index, uint64_t n,
                      float4* __restrict__ out) {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
-        const uint64_t i = first_index + j;
-        const uint64_t pix = i / spp;
-        const uint32_t px = (uint32_t)(pix % W), py = (uint32_t)((pix / W) % H);
+    uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    // where this thread starts
+    uint64_t i = first_index + j;
+    const uint64_t pix0 = i / spp;
+    uint32_t sp = (uint32_t)(i - pix0 * spp);
+    uint32_t px = (uint32_t)(pix0 % W), py = (uint32_t)((pix0 / W) % H);
+    // stride = ((d_py * W) + d_px) * spp + d_sp  (mod W H spp)
+    const uint64_t spix = stride / spp;
+    const uint32_t d_sp = (uint32_t)(stride - spix * spp);
+    const uint32_t d_px = (uint32_t)(spix % W), d_py = (uint32_t)((spix / W) % H);
+    const float inv24 = 1.0f / 16777216.0f;
+    const float fW = (float)W, fH = (float)H, aspect = xdiv(fH, fW);
+    for (;;) {
         const uint64_t g0 = mix64((seed ^ 0xA5A5A5A55A5A5A5Aull) + ZOICB_GOLDEN * (i + 1));
         const uint64_t g1 = mix64(g0 + ZOICB_GOLDEN);
-        const float inv24 = 1.0f / 16777216.0f;
         const float u0 = xmul((float)(uint32_t)(g0 & 0xFFFFFF), inv24);
         const float u1 = xmul((float)(uint32_t)((g0 >> 32) & 0xFFFFFF), inv24);
         const float u2 = xmul((float)(uint32_t)(g1 & 0xFFFFFF), inv24);
@@ -238,11 +250,22 @@ synth_samples_kernel(uint32_t W, uint32_t H, uint32_t spp, uint64_t seed, uint64
         const float fx = xadd((float)px, u0);
         const float fy = xadd((float)py, u1);
         float4 o;
-        o.x = xsub(xdiv(xmul(2.0f, fx), (float)W), 1.0f);
-        o.y = xmul(xsub(1.0f, xdiv(xmul(2.0f, fy), (float)H)), xdiv((float)H, (float)W));
+        o.x = xsub(xdiv(xmul(2.0f, fx), fW), 1.0f);
+        o.y = xmul(xsub(1.0f, xdiv(xmul(2.0f, fy), fH)), aspect);
         o.z = u2;
         o.w = u3;
         out[j] = o;
+        j += stride;
+        if (j >= n) break;
+        i += stride;
+        sp += d_sp;
+        uint32_t carry = 0;
+        if (sp >= spp) { sp -= spp; carry = 1; }
+        px += d_px + carry;
+        carry = 0;
+        if (px >= W) { px -= W; carry = 1; }
+        py += d_py + carry;
+        if (py >= H) py -= H;
     }
 }
 
@@ -487,6 +510,15 @@ static cudaError_t launch_variant(const CameraState& cam, int mode, const float4
         // costs, and the pool's shared-memory traffic made it slower, 12.4-15.0 against 17.6 Grays/s; profiles/r01b_ab.txt)
         cudaError_t e = cudaMemsetAsync(ws.counters, 0, 4 * sizeof(unsigned long long), st);
         if (e != cudaSuccess) return e;
+        // the column tables of an image-shaped aperture live in L1 / L2: ask for the smallest shared-memory carve-out that
+        // still holds the resident CTAs' row tables, so that L1 gets the rest of the 256 KB
+        static const int carve = [] { const char* v = getenv("ZOICB_THIN_CARVEOUT"); return v ? atoi(v) : -1; }();
+        if (kImage) {
+            const size_t need = (size_t)ZOICB_THIN_CTAS * (smem + 2200);
+            int pct = (int)((need * 100 + 233471) / 233472);
+            if (carve >= 0) pct = carve;
+            cudaFuncSetAttribute(thin_persistent_kernel<kImage>, cudaFuncAttributePreferredSharedMemoryCarveout, pct > 100 ? 100 : pct);
+        }
         thin_persistent_kernel<kImage><<<(unsigned)sm_count() * ZOICB_THIN_CTAS, threads, smem, st>>>(cam, samples, n, first_index, seed, rays,
                                                                                       stats, stage, ws.counters);
         if (launches) *launches += 1;
@@ -522,8 +554,8 @@ cudaError_t launch_generate(const CameraState& cam, int mode, const float4* samp
     const bool image = cam.use_image != 0;
     size_t smem = 0;
     int stage = 0;
-    if (image) {  // row-indexed tables staged in shared memory (kernel_common.cuh); zoicb_create rejects images with more than kMaxBokehRows rows
-        smem = bokeh_smem_bytes(cam.bokeh.w, cam.bokeh.h, cam.bokeh.row_shift);
+    if (image) {  // row tables staged in shared memory; zoicb_create rejects images with more than kMaxBokehRows rows
+        smem = bokeh_smem_bytes(cam.bokeh.h);
         stage = 1;
     }
 #define ZL(M, I, U) launch_variant<M, I, U>(cam, mode, samples, n, first_index, seed, rays, stats, st, ws, smem, stage, launches)
@@ -548,7 +580,7 @@ cudaError_t launch_draw_paths(const CameraState& cam, const float4* samples, uin
     if (n == 0) return cudaSuccess;
     const unsigned grid = (n + 127) / 128;
     const bool image = cam.use_image != 0, lut = cam.lens.use_lut != 0;
-    const size_t rows_smem = image ? bokeh_smem_bytes(cam.bokeh.w, cam.bokeh.h, cam.bokeh.row_shift) : 0;
+    const size_t rows_smem = image ? bokeh_smem_bytes(cam.bokeh.h) : 0;
 #define ZD(I, U) draw_paths_kernel<I, U><<<grid, 128, rows_smem, st>>>(cam, samples, n, indices, first_index, seed, quads, kinds, counts, cap)
     if (image) { if (lut) ZD(true, true); else ZD(true, false); }
     else { if (lut) ZD(false, true); else ZD(false, false); }

@@ -229,10 +229,10 @@ kolb_pool2_kernel(const __grid_constant__ CameraState cam, const float4* __restr
                   uint64_t first_index, uint64_t seed, RayRecord* __restrict__ rays,
                   DeviceStats* stats, unsigned long long* chunk_counter, unsigned long long* queue,
                   unsigned long long* queue_count, unsigned long long capacity, uint64_t queue_base) {
-    // dynamic shared memory: [bokeh row tables (bokeh_smem_bytes, 16-byte aligned)] [element table] [one WarpPool2 per warp]
+    // dynamic shared memory: [bokeh row tables (2h floats, 16-byte aligned)] [element table] [one WarpPool2 per warp]
     BokehView bk;
     if (kImage) bk = stage_bokeh(cam);
-    const unsigned rows_bytes = kImage ? bokeh_smem_bytes(cam.bokeh.w, cam.bokeh.h, cam.bokeh.row_shift) : 0u;
+    const unsigned rows_bytes = kImage ? bokeh_smem_bytes(cam.bokeh.h) : 0u;
     const LensState& L = cam.lens;
     float4* elems = reinterpret_cast<float4*>(reinterpret_cast<char*>(s_rows) + rows_bytes);
     for (int i = threadIdx.x; i < 4 * kMaxElements; i += blockDim.x) elems[i] = reinterpret_cast<const float4*>(L.e)[i];
