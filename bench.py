@@ -10,7 +10,7 @@ samples.  The default workload is the headline metric of BASELINE.json: the Kolb
 3840x2160x256spp frame (2.12 G rays), laid out in 8 passes of 32 spp (zoic_b200/workloads.py) and STRONG-split over the
 GPUs: rank r of G generates passes [r 8/G, (r+1) 8/G) = samples [r N/G, (r+1) N/G) of the one fixed job.
   * a share that fits in HBM is resident (16 B/sample in, 32 B/ray out) and a step is ONE zoicb_generate over it;
-  * a share that does not (config 4: 204 GB, config 5: 1.6 TB per lens) is STREAMED by zoicb_run_job: tiles of 2^27
+  * a share that does not (config 4: 204 GB, config 5: 1.6 TB per lens) is STREAMED by zoicb_run_job: tiles of 2^28
     samples synthesised on the device, generated, consumed by a checksum kernel, through rotating buffers.
 At N > 1 the line also carries `gather`: the same job with the final gather of every ray to rank 0 over NVLink
 (libzoicb's gather-to-consumer: kernels storing into rank 0's memory / copy-engine push / ncclSend-Recv), sequential and
@@ -278,7 +278,7 @@ def main():
     ap.add_argument("--samples", type=int, default=0, help="override samples per GPU per step (debug)")
     ap.add_argument("--spp", type=int, default=0, help="override samples per pixel (profiling: a small job that still covers the whole film)")
     ap.add_argument("--stream", action="store_true", help="stream the job through zoicb_run_job even if it would fit in HBM")
-    ap.add_argument("--tile-log2", type=int, default=27, help="streamed jobs: samples per tile")
+    ap.add_argument("--tile-log2", type=int, default=28, help="streamed jobs: samples per tile")
     ap.add_argument("--serial", action="store_true", help="streamed jobs: one stream, no overlap of synthesis / generation / consumption (A/B)")
     ap.add_argument("--e2e-samples", type=int, default=1 << 27)
     ap.add_argument("--cpu-samples", type=int, default=1 << 25, help="CPU baseline sample size (all cores)")

@@ -231,7 +231,7 @@ typedef struct zoicb_job {
     int32_t census;
     uint64_t sample_seed, rng_seed;
     uint64_t first, count;
-    uint64_t tile;                  /* samples per tile, 0 = 2^27 */
+    uint64_t tile;                  /* samples per tile, 0 = 2^28 */
     float census_tol;               /* 0 = 1e-5 (north-star tolerance) */
     int32_t n_windows;
     const uint64_t* window_first;

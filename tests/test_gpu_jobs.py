@@ -196,7 +196,7 @@ def _full_size_names():
 
 @pytest.mark.parametrize("name", _full_size_names())
 def test_full_size_streamed_jobs(port, name):
-    """Every sample of the configuration through zoicb_run_job (tiles of 2^27 synthesised on the device, generated,
+    """Every sample of the configuration through zoicb_run_job (tiles of 2^28 synthesised on the device, generated,
     consumed): all records consumed, counters consistent; three 2^16-sample windows (start, a tile boundary in the middle,
     end) equal to their own small launches bit for bit and to the oracle; the census of the first 2.1 G rays (GUARDED vs
     EXACT, every record): no flips, nothing out of tolerance."""
@@ -206,7 +206,7 @@ def test_full_size_streamed_jobs(port, name):
     if int(os.environ.get("ZOICB_TEST_MAX_SAMPLES", "0")):
         n = min(n, int(os.environ["ZOICB_TEST_MAX_SAMPLES"]))
     cam = ZoicCamera(**wl.params)
-    tile, wc = 1 << 27, 1 << 16
+    tile, wc = 1 << 28, 1 << 16
     mid = (n // tile // 2) * tile
     windows = [0, max(mid, wc) - wc // 2, n - wc]
     res = cam.run_job(*wl.synth_args(), wl.seed, 0, n, tile=tile, windows=windows, window_count=wc)

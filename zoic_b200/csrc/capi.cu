@@ -157,7 +157,7 @@ cudaError_t zoicb::api_get_workspace(zoicb_ctx* c, cudaStream_t st, uint64_t n, 
             w.queue = nullptr;
             w.capacity = 0;
         }
-        if ((e = cudaMalloc(&w.queue, want * sizeof(unsigned long long))) != cudaSuccess) return e;
+        if ((e = cudaMalloc(&w.queue, want * sizeof(QueueRecord))) != cudaSuccess) return e;
         w.capacity = want;
     }
     *out = w;

@@ -9,6 +9,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
@@ -342,6 +343,11 @@ int choose_split(const LensState& L, float sensor_w, float sensor_h, int* inner_
             total += 1.0;
             if (rc == kPass) pass += 1.0; else stop_at[visited - 1] += 1.0;
         }
+    }
+    if (std::getenv("ZOICB_DEBUG_SPLIT")) {   // calibration histogram: share of attempts stopped at each surface
+        std::fprintf(stderr, "[zoicb] attempts %.0f pass %.4f stop_at:", total, pass / total);
+        for (int i = 0; i < n; ++i) std::fprintf(stderr, " %d:%.4f", i, stop_at[i] / total);
+        std::fprintf(stderr, "\n");
     }
     if (pass < 1.0) pass = 1.0;
     const double setup = 130.0, per_surface = 66.0;

@@ -226,7 +226,7 @@ struct JobBuffers {
         const uint64_t want = cap / 24 + 4096;   // room for the undecided samples of a tile (capi.cu: api_get_workspace)
         if (want > cap_queue) {
             cudaFree(ws.queue); ws.queue = nullptr; cap_queue = 0;
-            if ((e = cudaMalloc(&ws.queue, want * sizeof(unsigned long long))) != cudaSuccess) return e;
+            if ((e = cudaMalloc(&ws.queue, want * sizeof(QueueRecord))) != cudaSuccess) return e;
             cap_queue = want;
         }
         ws.capacity = cap_queue;
@@ -248,7 +248,7 @@ extern "C" zoicb_status zoicb_run_job(zoicb_ctx* ctx, const zoicb_job* job, zoic
     ZGUARD(ctx->device);
     zoicb_gather* g = job->gather;
     const bool gathered = g != nullptr;
-    uint64_t tile = job->tile ? job->tile : (1ull << 27);
+    uint64_t tile = job->tile ? job->tile : (1ull << 28);
     if (gathered) {
         if (gather_device(g) != ctx->device) return api_fail(ZOICB_ERR_INVALID_ARGUMENT, "zoicb_run_job: gather and camera live on different devices");
         if (job->census) return api_fail(ZOICB_ERR_UNSUPPORTED, "zoicb_run_job: the census runs on ungathered jobs");

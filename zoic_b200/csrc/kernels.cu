@@ -48,7 +48,7 @@ __global__ void __launch_bounds__(256, 3)
 kolb_exact_persistent_kernel(const __grid_constant__ CameraState cam, const float4* __restrict__ samples, uint64_t m_direct,
                              uint64_t first_index, uint64_t seed, RayRecord* __restrict__ rays,
                              DeviceStats* stats, unsigned long long* cursor,
-                             const unsigned long long* __restrict__ queue, const unsigned long long* __restrict__ queue_count,
+                             const QueueRecord* __restrict__ queue, const unsigned long long* __restrict__ queue_count,
                              unsigned long long capacity) {
     BokehView bk;
     if (kImage) bk = stage_bokeh(cam);
@@ -82,15 +82,31 @@ kolb_exact_persistent_kernel(const __grid_constant__ CameraState cam, const floa
             const unsigned take = want < avail ? want : avail;
             const unsigned rank = __popc(need & lt_mask);
             if (!have && rank < take) {
-                idx = kQueued ? queue[cur + rank] : cur + rank;
+                unsigned packed = 0;
+                if (kQueued) {
+                    const QueueRecord q = queue[cur + rank];
+                    idx = q.index;
+                    packed = q.packed;
+                } else {
+                    idx = cur + rank;
+                }
                 const float4 s = samples[idx];
                 k = kolb_sample_setup<kLut, true>(L, s.x, s.y);
                 rng = sample_stream(seed, first_index + idx);
                 ua = s.z;
                 ub = s.w;
                 tries = 0;
+                if (kQueued) {
+                    // resume at the attempt the fast path could not decide: its earlier attempts were stopped for certain,
+                    // so only their draws and their counters are needed (kolb_pool2.cu: enqueue2)
+                    tries = (int)(packed & 0xffu);
+                    for (int t = 0; t < tries; ++t) draw_pair(rng, &ua, &ub);
+                    ls.attempts += (unsigned)tries;
+                    ls.tir += (packed >> 8) & 0xffu;
+                    ls.visits += packed >> 16;
+                }
                 have = true;
-                fresh = true;
+                fresh = true;   // the lens sample of this attempt is in (ua, ub) already
                 ls.rays++;
                 if (kQueued) ls.reruns++;
             }
@@ -106,7 +122,7 @@ kolb_exact_persistent_kernel(const __grid_constant__ CameraState cam, const floa
             lens_sample<kImage>(bk, ua, ub, &lx, &ly);
             Ray r;
             r.o = vmake(k.fx, k.fy, L.origin_shift);
-            r.d = kolb_aim<kLut>(L, k, lx, ly, !fresh);
+            r.d = kolb_aim<kLut>(L, k, lx, ly, tries > 0);   // the retry arithmetic from the first re-sample on (:1933)
             fresh = false;
             int visited;
             const int rc = exact_march(L, r, &visited);

@@ -9,12 +9,21 @@ namespace zoicb {
 
 struct alignas(32) RayRecord { float4 origin_w; float4 dir_tries; };   // = zoicb_ray (include/zoicb.h)
 
+// One undecided sample of the guarded kernel, handed to the exact kernel.  The attempts before `tries` were decided
+// (stopped for certain) by the fast path, so the exact kernel RESUMES at attempt `tries`: it advances the sample's retry
+// stream by that many draw pairs and adds the counters of the earlier attempts instead of marching them again.
+struct alignas(16) QueueRecord {
+    unsigned long long index;   // sample index within the generate call
+    uint32_t packed;            // tries [0..7] | total internal reflections [8..15] | element visits [16..31] of the decided attempts
+    uint32_t pad;
+};
+
 // Per-stream scratch: counters[0] = chunk cursor of the main kernel, counters[1] = number of queued (undecided)
-// sample indices, counters[2] = work cursor of the exact persistent kernel, counters[3] spare;
-// queue[capacity] = the undecided sample indices.
+// samples, counters[2] = work cursor of the exact persistent kernel, counters[3] spare;
+// queue[capacity] = the undecided samples.
 struct Workspace {
     unsigned long long* counters;
-    unsigned long long* queue;
+    QueueRecord* queue;
     unsigned long long capacity;
 };
 

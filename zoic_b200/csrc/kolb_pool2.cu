@@ -227,7 +227,7 @@ template <int kN, int kSplit, bool kImage, bool kLut, bool kInner, bool kPre = f
 __global__ void __launch_bounds__(kWarps2 * 32, PoolShape<(kInner || kImage || kSplit < 0)>::kCtas)
 kolb_pool2_kernel(const __grid_constant__ CameraState cam, const float4* __restrict__ samples, uint32_t n,
                   uint64_t first_index, uint64_t seed, RayRecord* __restrict__ rays,
-                  DeviceStats* stats, unsigned long long* chunk_counter, unsigned long long* queue,
+                  DeviceStats* stats, unsigned long long* chunk_counter, QueueRecord* queue,
                   unsigned long long* queue_count, unsigned long long capacity, uint64_t queue_base) {
     // dynamic shared memory: [bokeh row tables (2h floats, 16-byte aligned)] [element table] [one WarpPool2 per warp]
     BokehView bk;
@@ -280,8 +280,10 @@ kolb_pool2_kernel(const __grid_constant__ CameraState cam, const float4* __restr
         ls.visits += pk2_visits(packed);
         ls.tir += pk2_tir(packed);
     };
-    // undecided samples go to the exact re-run queue (one atomic per warp for both rays of every lane)
-    auto enqueue2 = [&](bool u0, uint32_t idx0, bool u1, uint32_t idx1) {
+    // undecided samples go to the exact re-run queue (one atomic per warp for both rays of every lane).  `before` = the
+    // packed counters of the attempts BEFORE the undecided one (tries = its number; the visits of the undecided attempt
+    // itself taken out again): the exact kernel resumes there instead of repeating the decided attempts.
+    auto enqueue2 = [&](bool u0, uint32_t idx0, unsigned before0, bool u1, uint32_t idx1, unsigned before1) {
         const unsigned m0 = __ballot_sync(0xffffffffu, u0);
         const unsigned m1 = __ballot_sync(0xffffffffu, u1);
         if ((m0 | m1) == 0u) return;
@@ -293,9 +295,14 @@ kolb_pool2_kernel(const __grid_constant__ CameraState cam, const float4* __restr
             const bool u = h ? u1 : u0;
             if (!u) continue;
             const uint32_t idx = h ? idx1 : idx0;
+            const unsigned before = h ? before1 : before0;
             const unsigned long long pos = base + (h ? __popc(m0) + __popc(m1 & lt_mask) : __popc(m0 & lt_mask));
             if (pos < capacity) {
-                queue[pos] = queue_base + idx;
+                QueueRecord q;
+                q.index = queue_base + idx;
+                q.packed = pk2_tries(before) | (pk2_tir(before) << 8) | (pk2_visits(before) << 16);
+                q.pad = 0;
+                queue[pos] = q;
             } else {  // queue full: settle it here, exactly
                 float4 o4, d4;
                 kolb_exact_sample<kImage, kLut>(cam, bk, samples[idx], first_index + idx, seed, &o4, &d4, ls);
@@ -404,7 +411,8 @@ kolb_pool2_kernel(const __grid_constant__ CameraState cam, const float4* __restr
                     emit(h ? slot1 : slot0, h ? idx1 : idx0, packed, half_of(r.ox, h), half_of(r.oy, h), half_of(r.oz, h), half_of(r.ux, h),
                          half_of(r.uy, h), half_of(r.uz, h));
             }
-            enqueue2(und[0], idx0, und[1], idx1);
+            // the undecided attempt's own visits: its stage-A share (all `split` surfaces) + what stage B walked
+            enqueue2(und[0], idx0, packed0 - ((unsigned)(v0 + split) << 16), und[1], idx1, packed1 - ((unsigned)(v1 + split) << 16));
             nA = push2(P.qa, nA, again[0], slot0, again[1], slot1);
             nF = push2(P.qf, nF, done[0] || und[0], slot0, done[1] || und[1], slot1);
             __syncwarp();
@@ -431,6 +439,7 @@ kolb_pool2_kernel(const __grid_constant__ CameraState cam, const float4* __restr
             Xor128 g0 = {ga.x, ga.y, ga.z, ga.w}, g1 = {gb.x, gb.y, gb.z, gb.w};
             RayPair r = {fx, fy, bc(L.origin_shift), bc(0.0f), bc(0.0f), bc(1.0f)};
             int rc0 = kPass, rc1 = kPass;
+            int lastv0 = 0, lastv1 = 0;        // surfaces the ray's latest attempt of this pass visited
             bool todo0 = act0, todo1 = act1;   // rays that still owe an attempt in this pass
             // While at least half the rays of the pass were stopped inside stage A, those rays re-sample right here
             // instead of going round through the stacks (the cheap path for cameras whose attempts mostly die at the
@@ -483,8 +492,8 @@ kolb_pool2_kernel(const __grid_constant__ CameraState cam, const float4* __restr
                 } else {
                     march_pair<kN, kInner>(elems, cam.guard_scale, 0, split, a, todo0, todo1, &nrc0, &nrc1, &v0, &v1);
                 }
-                if (todo0) { rc0 = nrc0; packed0 += (unsigned)v0 << 16; if (nrc0 == kTir) packed0 += 1u << 9; fresh0 = false; }
-                if (todo1) { rc1 = nrc1; packed1 += (unsigned)v1 << 16; if (nrc1 == kTir) packed1 += 1u << 9; fresh1 = false; }
+                if (todo0) { rc0 = nrc0; lastv0 = v0; packed0 += (unsigned)v0 << 16; if (nrc0 == kTir) packed0 += 1u << 9; fresh0 = false; }
+                if (todo1) { rc1 = nrc1; lastv1 = v1; packed1 += (unsigned)v1 << 16; if (nrc1 == kTir) packed1 += 1u << 9; fresh1 = false; }
                 if (kPre) {   // the origin stays the film point; only the direction of a re-sampled ray changes
                     r.ux = mk(todo0 ? lo(a.ux) : lo(r.ux), todo1 ? hi(a.ux) : hi(r.ux));
                     r.uy = mk(todo0 ? lo(a.uy) : lo(r.uy), todo1 ? hi(a.uy) : hi(r.uy));
@@ -530,7 +539,7 @@ kolb_pool2_kernel(const __grid_constant__ CameraState cam, const float4* __restr
                     emit(slot, idx, packed, half_of(r.ox, h), half_of(r.oy, h), half_of(r.oz, h), half_of(r.ux, h), half_of(r.uy, h),
                          half_of(r.uz, h));
             }
-            enqueue2(und[0], idx0, und[1], idx1);
+            enqueue2(und[0], idx0, packed0 - ((unsigned)lastv0 << 16), und[1], idx1, packed1 - ((unsigned)lastv1 << 16));
             nA = push2(P.qa, nA, again[0], slot0, again[1], slot1);
             nB = push2(P.qb, nB, onward[0], slot0, onward[1], slot1);
             nF = push2(P.qf, nF, done[0] || und[0], slot0, done[1] || und[1], slot1);
