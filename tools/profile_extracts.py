@@ -38,16 +38,54 @@ keep = ("gpu__time_duration.sum", "smsp__inst_executed.sum", "smsp__issue_active
         "sm__inst_executed_pipe_lsu", "sm__inst_executed_pipe_fma", "sm__inst_executed_pipe_alu", "dram__bytes", "dram__throughput", "gpu__dram_throughput",
         "smsp__warps_eligible", "smsp__warp_issue_stalled", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared", "lts__t_sector_hit_rate",
         "smsp__sass_thread_inst_executed_op_ffma", "smsp__sass_thread_inst_executed_op_fp32", "sm__sass_thread_inst_executed_op_f", "smsp__inst_executed_op")
-for cap, out in ((tag + "_ncu_pool2.ncu-rep", name + "_ncu_main_raw.csv"), (tag + "_ncu_rerun.ncu-rep", name + "_ncu_rerun_raw.csv")):
+keep = keep + ("l1tex__t_sector", "l1tex__t_sectors_pipe_lsu_mem_global_op_ld", "l1tex__data_pipe_lsu_wavefronts", "lts__t_sector_op_read_hit_rate")
+for cap, out in ((tag + "_ncu_pool2.ncu-rep", name + "_ncu_main_raw.csv"), (tag + "_ncu_rerun.ncu-rep", name + "_ncu_rerun_raw.csv"),
+                 (tag + "_ncu_thin.ncu-rep", name + "_ncu_thin_raw.csv")):
     path = os.path.join(G, cap)
     if not os.path.exists(path): continue
     raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     r = list(csv.reader(io.StringIO(raw)))
     hdr, units, vals = r[0], r[1], r[2]
     with open(os.path.join(P, out), "w") as f:
-        f.write("# ncu --set full --clock-control none --import-source on, python bench.py --spp 4 --steps 1 --warmup 2 (33 M rays over the whole film); kernel: %s\n" % vals[hdr.index("Kernel Name")][:120])
+        f.write("# ncu --set full --clock-control none --import-source on, python bench.py --spp 8 (config3: 32) --steps 1 --warmup 2 (a whole-film batch); kernel: %s\n" % vals[hdr.index("Kernel Name")][:120])
         f.write("metric,unit,value\n")
         for h, u, v in zip(hdr, units, vals):
             if any(h.startswith(k) for k in keep) and "realtime" not in h and ".max" not in h and ".min" not in h:
                 f.write("%s,%s,%s\n" % (h, u, v))
     print("wrote", out)
+
+# 3. traffic.json: DRAM bytes per ray of the dominant kernels, tied to the source they were captured from (bench.py refuses a
+# capture whose kernel source has changed since)
+import hashlib
+def sha(path): return hashlib.sha1(open(path, "rb").read()).hexdigest()[:12]
+commit = subprocess.run(["git", "rev-parse", "--short", "HEAD"], capture_output=True, text=True).stdout.strip()
+traffic = {}
+def per_ray(csv_path, kernel_sub, rays):
+    rows = [r for r in csv.reader(open(csv_path, errors="replace")) if len(r) > 14 and r[0].isdigit()]
+    by = defaultdict(dict)
+    for r in rows:
+        if kernel_sub in r[4]: by[int(r[0])][r[12]] = float(r[14])
+    if not by: return None
+    last = by[max(by)]
+    return (last.get("dram__bytes_read.sum", 0) + last.get("dram__bytes_write.sum", 0)) / rays, last
+hp = os.path.join(G, tag + "_launches_headline.csv")
+if os.path.exists(hp):
+    v = per_ray(hp, "kolb_pool2_kernel", 2123366400)
+    if v:
+        traffic["kolb"] = {"dram_bytes_per_ray": round(v[0], 3), "source": "kolb_pool2.cu", "source_sha1": sha("zoic_b200/csrc/kolb_pool2.cu"),
+                           "commit": commit, "capture": "profiles/%s_launches_headline.csv" % name,
+                           "what": "dram__bytes_read.sum + dram__bytes_write.sum of the last kolb_pool2_kernel launch (2,123,366,400 rays); algorithmic 48 B/ray"}
+cp = os.path.join(G, tag + "_launches_config3.csv")
+if os.path.exists(cp):
+    v = per_ray(cp, "thin_persistent_kernel", 2123366400)
+    if v:
+        traffic["thin_image"] = {"dram_bytes_per_ray": round(v[0], 3), "source": "kernels.cu", "source_sha1": sha("zoic_b200/csrc/kernels.cu"),
+                                 "commit": commit, "capture": "profiles/%s_launches_config3.csv" % name,
+                                 "what": "dram__bytes_read.sum + dram__bytes_write.sum of the last thin_persistent_kernel<1> launch (2,123,366,400 rays); algorithmic 48 B/ray"}
+    rows = [r for r in csv.reader(open(cp, errors="replace")) if len(r) > 14 and r[0].isdigit()]
+    with open(os.path.join(P, name + "_launches_config3.csv"), "w") as f:
+        f.write("# ncu launch list of: python bench.py --workload config3 --steps 2 --warmup 1 --no-cpu --no-e2e\nid,kernel,metric,value\n")
+        for r in rows: f.write("%s,%s,%s,%s\n" % (r[0], r[4].split("(")[0].replace("zoicb::", "").replace("void ", ""), r[12], r[14]))
+if traffic:
+    json.dump(traffic, open(os.path.join(P, "traffic.json"), "w"), indent=1)
+    print("wrote traffic.json", traffic)

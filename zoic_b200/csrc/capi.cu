@@ -304,6 +304,7 @@ zoicb_status zoicb_generate(zoicb_ctx* ctx, const void* d_samples, uint64_t n, u
     if (!d_samples || !d_rays) return api_fail(ZOICB_ERR_INVALID_ARGUMENT, "zoicb_generate: null buffer");
     if (((uintptr_t)d_rays & 31u) || ((uintptr_t)d_samples & 15u))
         return api_fail(ZOICB_ERR_INVALID_ARGUMENT, "zoicb_generate: samples must be 16-byte and rays 32-byte aligned");
+    if (n > (1ull << 40)) return api_fail(ZOICB_ERR_INVALID_ARGUMENT, "zoicb_generate: at most 2^40 samples per call (split the batch; first_index keeps the streams)");
     ZGUARD(ctx->device);
     int launches = 0;
     Workspace ws = {nullptr, nullptr, 0};

@@ -82,11 +82,10 @@ kolb_exact_persistent_kernel(const __grid_constant__ CameraState cam, const floa
             const unsigned take = want < avail ? want : avail;
             const unsigned rank = __popc(need & lt_mask);
             if (!have && rank < take) {
-                unsigned packed = 0;
+                QueueRecord q = 0;
                 if (kQueued) {
-                    const QueueRecord q = queue[cur + rank];
-                    idx = q.index;
-                    packed = q.packed;
+                    q = queue[cur + rank];
+                    idx = queue_index(q);
                 } else {
                     idx = cur + rank;
                 }
@@ -99,11 +98,11 @@ kolb_exact_persistent_kernel(const __grid_constant__ CameraState cam, const floa
                 if (kQueued) {
                     // resume at the attempt the fast path could not decide: its earlier attempts were stopped for certain,
                     // so only their draws and their counters are needed (kolb_pool2.cu: enqueue2)
-                    tries = (int)(packed & 0xffu);
+                    tries = (int)queue_tries(q);
                     for (int t = 0; t < tries; ++t) draw_pair(rng, &ua, &ub);
                     ls.attempts += (unsigned)tries;
-                    ls.tir += (packed >> 8) & 0xffu;
-                    ls.visits += packed >> 16;
+                    ls.tir += queue_tir(q);
+                    ls.visits += queue_visits(q);
                 }
                 have = true;
                 fresh = true;   // the lens sample of this attempt is in (ua, ub) already

@@ -9,14 +9,20 @@ namespace zoicb {
 
 struct alignas(32) RayRecord { float4 origin_w; float4 dir_tries; };   // = zoicb_ray (include/zoicb.h)
 
-// One undecided sample of the guarded kernel, handed to the exact kernel.  The attempts before `tries` were decided
-// (stopped for certain) by the fast path, so the exact kernel RESUMES at attempt `tries`: it advances the sample's retry
-// stream by that many draw pairs and adds the counters of the earlier attempts instead of marching them again.
-struct alignas(16) QueueRecord {
-    unsigned long long index;   // sample index within the generate call
-    uint32_t packed;            // tries [0..7] | total internal reflections [8..15] | element visits [16..31] of the decided attempts
-    uint32_t pad;
-};
+// One undecided sample of the guarded kernel, handed to the exact kernel: ONE 64-bit word (the pool kernel's stores and
+// register allocation are those of a plain index queue).  The attempts before `tries` were decided (stopped for certain)
+// by the fast path, so the exact kernel RESUMES at attempt `tries`: it advances the sample's retry stream by that many
+// draw pairs and adds the counters of the earlier attempts instead of marching them again.
+//   bits 0..39  sample index within the generate call (zoicb_generate takes at most 2^40 samples per call)
+//   bits 40..44 tries (<= 26)   bits 45..49 total internal reflections (<= 26)   bits 50..63 element visits (<= 26 x 24)
+typedef unsigned long long QueueRecord;
+__host__ __device__ inline QueueRecord queue_pack(unsigned long long index, unsigned tries, unsigned tir, unsigned visits) {
+    return index | ((unsigned long long)tries << 40) | ((unsigned long long)tir << 45) | ((unsigned long long)visits << 50);
+}
+__host__ __device__ inline unsigned long long queue_index(QueueRecord q) { return q & ((1ull << 40) - 1); }
+__host__ __device__ inline unsigned queue_tries(QueueRecord q) { return (unsigned)(q >> 40) & 31u; }
+__host__ __device__ inline unsigned queue_tir(QueueRecord q) { return (unsigned)(q >> 45) & 31u; }
+__host__ __device__ inline unsigned queue_visits(QueueRecord q) { return (unsigned)(q >> 50); }
 
 // Per-stream scratch: counters[0] = chunk cursor of the main kernel, counters[1] = number of queued (undecided)
 // samples, counters[2] = work cursor of the exact persistent kernel, counters[3] spare;

@@ -280,10 +280,11 @@ kolb_pool2_kernel(const __grid_constant__ CameraState cam, const float4* __restr
         ls.visits += pk2_visits(packed);
         ls.tir += pk2_tir(packed);
     };
-    // undecided samples go to the exact re-run queue (one atomic per warp for both rays of every lane).  `before` = the
-    // packed counters of the attempts BEFORE the undecided one (tries = its number; the visits of the undecided attempt
-    // itself taken out again): the exact kernel resumes there instead of repeating the decided attempts.
-    auto enqueue2 = [&](bool u0, uint32_t idx0, unsigned before0, bool u1, uint32_t idx1, unsigned before1) {
+    // undecided samples go to the exact re-run queue (one atomic per warp for both rays of every lane), with the packed
+    // counters of the attempts BEFORE the undecided one (tries = its number): the exact kernel resumes there instead of
+    // repeating the decided attempts.  The counters are read back from the slot (misc.w) inside the rare store, minus
+    // `sub` (stage B: the attempt's stage-A visits), so nothing extra stays live across the march.
+    auto enqueue2 = [&](bool u0, uint32_t idx0, int slot0, bool u1, uint32_t idx1, int slot1, unsigned sub) {
         const unsigned m0 = __ballot_sync(0xffffffffu, u0);
         const unsigned m1 = __ballot_sync(0xffffffffu, u1);
         if ((m0 | m1) == 0u) return;
@@ -295,14 +296,10 @@ kolb_pool2_kernel(const __grid_constant__ CameraState cam, const float4* __restr
             const bool u = h ? u1 : u0;
             if (!u) continue;
             const uint32_t idx = h ? idx1 : idx0;
-            const unsigned before = h ? before1 : before0;
             const unsigned long long pos = base + (h ? __popc(m0) + __popc(m1 & lt_mask) : __popc(m0 & lt_mask));
             if (pos < capacity) {
-                QueueRecord q;
-                q.index = queue_base + idx;
-                q.packed = pk2_tries(before) | (pk2_tir(before) << 8) | (pk2_visits(before) << 16);
-                q.pad = 0;
-                queue[pos] = q;
+                const unsigned before = __float_as_uint(P.misc[h ? slot1 : slot0].w) - sub;
+                queue[pos] = queue_pack(queue_base + idx, pk2_tries(before), pk2_tir(before), pk2_visits(before));
             } else {  // queue full: settle it here, exactly
                 float4 o4, d4;
                 kolb_exact_sample<kImage, kLut>(cam, bk, samples[idx], first_index + idx, seed, &o4, &d4, ls);
@@ -411,8 +408,9 @@ kolb_pool2_kernel(const __grid_constant__ CameraState cam, const float4* __restr
                     emit(h ? slot1 : slot0, h ? idx1 : idx0, packed, half_of(r.ox, h), half_of(r.oy, h), half_of(r.oz, h), half_of(r.ux, h),
                          half_of(r.uy, h), half_of(r.uz, h));
             }
-            // the undecided attempt's own visits: its stage-A share (all `split` surfaces) + what stage B walked
-            enqueue2(und[0], idx0, packed0 - ((unsigned)(v0 + split) << 16), und[1], idx1, packed1 - ((unsigned)(v1 + split) << 16));
+            // an undecided attempt is repeated from its start by the exact kernel: the counters before it are the ones the
+            // slot still holds (stage-B entry) minus the attempt's stage-A share (all `split` surfaces)
+            enqueue2(und[0], idx0, slot0, und[1], idx1, slot1, (unsigned)split << 16);
             nA = push2(P.qa, nA, again[0], slot0, again[1], slot1);
             nF = push2(P.qf, nF, done[0] || und[0], slot0, done[1] || und[1], slot1);
             __syncwarp();
@@ -535,11 +533,13 @@ kolb_pool2_kernel(const __grid_constant__ CameraState cam, const float4* __restr
                     }
                     P.misc[slot].w = __uint_as_float(packed);
                 }
+                // undecided: leave the counters of the attempts before this one in the slot for enqueue2
+                if (und[h]) P.misc[slot].w = __uint_as_float(packed - ((unsigned)(h ? lastv1 : lastv0) << 16));
                 if (done[h])
                     emit(slot, idx, packed, half_of(r.ox, h), half_of(r.oy, h), half_of(r.oz, h), half_of(r.ux, h), half_of(r.uy, h),
                          half_of(r.uz, h));
             }
-            enqueue2(und[0], idx0, packed0 - ((unsigned)lastv0 << 16), und[1], idx1, packed1 - ((unsigned)lastv1 << 16));
+            enqueue2(und[0], idx0, slot0, und[1], idx1, slot1, 0u);   // reads back the lane's own slot words written above
             nA = push2(P.qa, nA, again[0], slot0, again[1], slot1);
             nB = push2(P.qb, nB, onward[0], slot0, onward[1], slot1);
             nF = push2(P.qf, nF, done[0] || und[0], slot0, done[1] || und[1], slot1);
