@@ -147,6 +147,41 @@ def test_host_buffer_entry_point(port):
     ref.close()
 
 
+def test_two_host_threads_share_a_camera_and_a_stream(port):
+    """generate calls on one context from several host threads.  Two threads drive the SAME camera on the
+    SAME (default) stream, guarded mode (counter reset + pool kernel + re-run kernel per call): every call's records must
+    be those of a lone call -- the enqueue phases serialise on the context's lock, so no call sees another's cursor or
+    queue -- and growing the workspace under way (a larger batch in between) must not pull a queue from under a caller."""
+    import threading
+    from zoic_b200 import ZoicCamera
+    from zoic_b200.workloads import lens_path
+    cam = ZoicCamera(lensModel=1, lensDataPath=lens_path("fisheye_muller_f4.0.dat"), focalLength=1.0, fStop=4.0)
+    sizes = [70_000, 200_000, 90_000, 400_000]
+    batches = [torch.from_numpy(random_samples(n, seed=40 + k)).cuda() for k, n in enumerate(sizes)]
+    want = [cam.create_rays(b, seed=3, first_index=1000 * k).clone() for k, b in enumerate(batches)]
+    torch.cuda.synchronize()
+    errors = []
+
+    def worker(tid):
+        try:
+            for rep in range(12):
+                k = (rep + tid) % len(batches)
+                out = cam.create_rays(batches[k], seed=3, first_index=1000 * k)
+                torch.cuda.synchronize()
+                if not torch.equal(out.view(torch.int32), want[k].view(torch.int32)):
+                    errors.append((tid, rep, k))
+        except Exception as exc:   # noqa: BLE001
+            errors.append((tid, repr(exc)))
+
+    threads = [threading.Thread(target=worker, args=(t,)) for t in range(2)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    cam.close()
+
+
 def test_empty_batch_and_errors():
     from zoic_b200 import ZoicCamera, capi
     cam = ZoicCamera(lensModel=0, focalLength=3.5, fStop=2.8)
