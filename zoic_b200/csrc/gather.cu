@@ -166,6 +166,7 @@ struct zoicb_gather {
 namespace zoicb {
 
 int gather_device(const zoicb_gather* g) { return g->device; }
+int gather_rank(const zoicb_gather* g) { return g->rank; }
 uint64_t gather_tile_rays(const zoicb_gather* g) { return g->tile; }
 uint64_t gather_rounds(const zoicb_gather* g, const uint64_t* counts) {
     uint64_t r = 0;

@@ -9,6 +9,7 @@
 namespace zoicb {
 
 int gather_device(const zoicb_gather* g);
+int gather_rank(const zoicb_gather* g);
 uint64_t gather_tile_rays(const zoicb_gather* g);   // records every rank contributes per round (at most)
 // number of rounds all ranks run for these per-rank totals (counts[world], the same array on every rank)
 uint64_t gather_rounds(const zoicb_gather* g, const uint64_t* counts);

@@ -244,10 +244,10 @@ extern "C" zoicb_status zoicb_run_job(zoicb_ctx* ctx, const zoicb_job* job, zoic
     if (!job->W || !job->H || !job->spp_per_pass) return api_fail(ZOICB_ERR_INVALID_ARGUMENT, "zoicb_run_job: zero dimension");
     if (job->n_windows < 0 || (job->n_windows > 0 && (!job->window_first || !job->d_windows || !job->window_count)))
         return api_fail(ZOICB_ERR_INVALID_ARGUMENT, "zoicb_run_job: bad window arguments");
-    if (job->count == 0) return ZOICB_OK;
-    ZGUARD(ctx->device);
     zoicb_gather* g = job->gather;
     const bool gathered = g != nullptr;
+    if (job->count == 0 && !gathered) return ZOICB_OK;   // (a rank with an empty share still walks the rounds of a gathered job)
+    ZGUARD(ctx->device);
     uint64_t tile = job->tile ? job->tile : (1ull << 28);
     if (gathered) {
         if (gather_device(g) != ctx->device) return api_fail(ZOICB_ERR_INVALID_ARGUMENT, "zoicb_run_job: gather and camera live on different devices");
@@ -258,6 +258,8 @@ extern "C" zoicb_status zoicb_run_job(zoicb_ctx* ctx, const zoicb_job* job, zoic
     const uint64_t ntiles = (job->count + tile - 1) / tile;
     // all ranks of a gathered job run the same number of rounds (the consumer waits for every rank in every round)
     if (gathered && !job->gather_counts) return api_fail(ZOICB_ERR_INVALID_ARGUMENT, "zoicb_run_job: a gathered job needs gather_counts (every rank's sample count)");
+    if (gathered && job->gather_counts[gather_rank(g)] != job->count)
+        return api_fail(ZOICB_ERR_INVALID_ARGUMENT, "zoicb_run_job: gather_counts[this rank] differs from the job's count");
     const uint64_t rounds = gathered ? std::max<uint64_t>(ntiles, gather_rounds(g, job->gather_counts)) : ntiles;
 
     std::lock_guard<std::mutex> job_lock(ctx->job_mu);
