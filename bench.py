@@ -420,7 +420,9 @@ def main():
     traffic, traffic_note = None, None
     try:
         cap = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        key = "kolb" if model == 1 else ("thin_image" if wl.image() is not None else "thin")
+        # "thin" = the thin-lens retry kernel (thin_persistent_kernel: optical vignetting on); the single-attempt thin lens
+        # runs another kernel (exact_kernel), for which there is no capture
+        key = "kolb" if model == 1 else ("thin" if wl.params.get("opticalVignettingDistance", 0.0) > 0.0 else None)
         if key in cap:
             src = os.path.join(ROOT, "zoic_b200", "csrc", cap[key].get("source", "kolb_pool2.cu"))
             import hashlib

@@ -79,7 +79,7 @@ cp = os.path.join(G, tag + "_launches_config3.csv")
 if os.path.exists(cp):
     v = per_ray(cp, "thin_persistent_kernel", 2123366400)
     if v:
-        traffic["thin_image"] = {"dram_bytes_per_ray": round(v[0], 3), "source": "kernels.cu", "source_sha1": sha("zoic_b200/csrc/kernels.cu"),
+        traffic["thin"] = {"dram_bytes_per_ray": round(v[0], 3), "source": "kernels.cu", "source_sha1": sha("zoic_b200/csrc/kernels.cu"),
                                  "commit": commit, "capture": "profiles/%s_launches_config3.csv" % name,
                                  "what": "dram__bytes_read.sum + dram__bytes_write.sum of the last thin_persistent_kernel<1> launch (2,123,366,400 rays); algorithmic 48 B/ray"}
     rows = [r for r in csv.reader(open(cp, errors="replace")) if len(r) > 14 and r[0].isdigit()]
