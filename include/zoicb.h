@@ -193,6 +193,12 @@ ZOICB_API zoicb_status zoicb_differentials(zoicb_ctx* ctx, const void* d_samples
                                            uint64_t rng_seed, float dsx, float dsy, const zoicb_ray* d_rays,
                                            zoicb_ray_diff* d_out, void* stream);
 
+/* Camera -> world for the differentials: they are differences of points / of directions, so each of the four vectors is
+ * multiplied by the 3x3 part of the row-major 3x4 matrix (host memory), with the fma chain of zoicb_transform_rays'
+ * directions.  d_out may equal d_diffs. */
+ZOICB_API zoicb_status zoicb_transform_differentials(zoicb_ctx* ctx, const zoicb_ray_diff* d_diffs, uint64_t n,
+                                                     const float* m3x4, zoicb_ray_diff* d_out, void* stream);
+
 /* draw.zoic writer: the file the reference's -D_DRAW build leaves for src/draw.py
  * (writeToFile, src/zoic.cpp:1240-1293, and the DRAW_ONLY blocks of traceThroughLensElements :1121-1128,
  * :1146-1153): "LENSMODEL{KOLB}", the lens cross-section header, then "RAYS{...}" with the (z, y) path of every

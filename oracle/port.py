@@ -51,6 +51,7 @@ def load():
                                         C.c_void_p]
     lib.zport_sample_stream.argtypes = [C.c_uint64, C.c_uint64, C.c_void_p]
     lib.zport_transform_rays.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
+    lib.zport_transform_differentials.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
     lib.zport_differentials.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_float, C.c_float,
                                         C.c_void_p, C.c_void_p, C.c_void_p]
     lib.zport_get_constants.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
@@ -71,6 +72,15 @@ def transform_rays(rays, camera_to_world):
     m = np.ascontiguousarray(np.asarray(camera_to_world, np.float32).reshape(12))
     out = np.empty_like(rays)
     load().zport_transform_rays(rays.ctypes.data, rays.shape[0], m.ctypes.data, out.ctypes.data)
+    return out
+
+
+def transform_differentials(diffs, camera_to_world):
+    """CPU statement of zoicb_transform_differentials: [n, 12] differentials times the 3x3 part of the 3x4 matrix."""
+    d = np.ascontiguousarray(diffs, np.float32).reshape(-1, 12)
+    m = np.ascontiguousarray(np.asarray(camera_to_world, np.float32).reshape(12))
+    out = np.empty_like(d)
+    load().zport_transform_differentials(d.ctypes.data, d.shape[0], m.ctypes.data, out.ctypes.data)
     return out
 
 

@@ -923,6 +923,17 @@ void zport_differentials(void* c, const float* samples, uint64_t n, uint64_t fir
     }
 }
 
+// Camera -> world for the differentials (contract of zoicb_transform_differentials): every one of the four vectors times
+// the 3x3 part of the row-major 3x4 matrix, v'_r = fma(m[r][0], vx, fma(m[r][1], vy, m[r][2] * vz)).
+void zport_transform_differentials(const float* diffs, uint64_t n, const float* m, float* out) {
+    for (uint64_t i = 0; i < n; ++i)
+        for (int k = 0; k < 4; ++k) {
+            const float* v = diffs + 12 * i + 3 * k;
+            float* o = out + 12 * i + 3 * k;
+            for (int r = 0; r < 3; ++r) o[r] = fmaf(m[4 * r], v[0], fmaf(m[4 * r + 1], v[1], m[4 * r + 2] * v[2]));
+        }
+}
+
 // Derived camera state for host-side parity tests.
 //   scalars[16]: fov, tan_fov, apertureRadius, userApertureRadius, originShift, apertureDistance,
 //                focalLengthRatio, tracedFocalLength[0..1], principalPlane[0..1], focalPoint[0..1],

@@ -166,6 +166,13 @@ def test_ray_differentials_match_the_contract(port):
         live = ~dead
         assert np.isfinite(want).all() and np.abs(want[live, 6:]).max() < 0.05     # a pixel's worth of direction change
         assert (np.abs(want[live, 6:9]).sum(1) > 0).mean() > 0.95                   # and almost never stopped
+        # camera -> world: every differential vector times the 3x3 part of the matrix, bit for bit; in place too
+        m = np.random.default_rng(7).normal(size=(3, 4)).astype(np.float32)
+        world = cam.transform_differentials(got, m)
+        assert bits_equal(world.cpu().numpy(), port.transform_differentials(want, m))
+        same = got.clone()
+        cam.transform_differentials(same, m, out=same)
+        assert torch.equal(same.view(torch.int32), world.view(torch.int32))
         cam.set_mode(MODE_EXACT)
         rays_x = cam.create_rays(s, seed=5, first_index=first)
         got_x = cam.differentials(s, rays_x, dsx, dsy, seed=5, first_index=first)

@@ -221,6 +221,20 @@ class ZoicCamera:
                                                 rays.data_ptr(), out.data_ptr(), C.c_void_p(stream)))
         return out
 
+    def transform_differentials(self, diffs, camera_to_world, out=None, stream=None):
+        """Camera -> world for ray differentials [n, 12]: every vector times the 3x3 part of the 3x4 matrix."""
+        import torch
+        assert diffs.is_cuda and diffs.dtype == torch.float32 and diffs.is_contiguous()
+        m = np.ascontiguousarray(np.asarray(camera_to_world, dtype=np.float32).reshape(12))
+        n = diffs.numel() // 12
+        if out is None:
+            out = torch.empty_like(diffs)
+        if stream is None:
+            stream = torch.cuda.current_stream(diffs.device).cuda_stream
+        capi.check(self.lib.zoicb_transform_differentials(self.ctx, diffs.data_ptr(), n, m.ctypes.data, out.data_ptr(),
+                                                          C.c_void_p(stream)))
+        return out
+
     def synth_samples(self, W, H, spp, seed, first_index, n, out=None, stream=None):
         """Synthetic (sx, sy, lensx, lensy) samples generated on the device."""
         import torch

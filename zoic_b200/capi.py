@@ -91,6 +91,7 @@ SYMBOLS = {
     "zoicb_write_draw_file": (C.c_int, [_P, C.c_char_p, _P, C.c_uint32, _P, C.c_uint64, C.c_uint64]),
     "zoicb_transform_rays": (C.c_int, [_P, _P, C.c_uint64, _P, _P, _P]),
     "zoicb_differentials": (C.c_int, [_P, _P, C.c_uint64, C.c_uint64, C.c_uint64, C.c_float, C.c_float, _P, _P, _P]),
+    "zoicb_transform_differentials": (C.c_int, [_P, _P, C.c_uint64, _P, _P, _P]),
     "zoicb_synth_samples": (C.c_int, [_P, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint64, _P, _P]),
     "zoicb_get_stats": (C.c_int, [_P, C.POINTER(Stats)]),
     "zoicb_reset_stats": (C.c_int, [_P]),

@@ -548,6 +548,21 @@ zoicb_status zoicb_differentials(zoicb_ctx* ctx, const void* d_samples, uint64_t
     return ZOICB_OK;
 }
 
+zoicb_status zoicb_transform_differentials(zoicb_ctx* ctx, const zoicb_ray_diff* d_diffs, uint64_t n, const float* m3x4,
+                                           zoicb_ray_diff* d_out, void* stream) {
+    if (!ctx) return api_fail(ZOICB_ERR_INVALID_ARGUMENT, "zoicb_transform_differentials: null context");
+    if (n == 0) return ZOICB_OK;
+    if (!d_diffs || !d_out || !m3x4) return api_fail(ZOICB_ERR_INVALID_ARGUMENT, "zoicb_transform_differentials: null argument");
+    if (((uintptr_t)d_diffs & 15u) || ((uintptr_t)d_out & 15u))
+        return api_fail(ZOICB_ERR_INVALID_ARGUMENT, "zoicb_transform_differentials: differentials must be 16-byte aligned");
+    ZGUARD(ctx->device);
+    int launches = 0;
+    cudaError_t e = launch_transform_diffs(m3x4, (const float4*)d_diffs, n, (float4*)d_out, (cudaStream_t)stream, &launches);
+    api_count_launches(launches);
+    if (e != cudaSuccess) return api_cuda_fail(e, "zoicb_transform_differentials launch");
+    return ZOICB_OK;
+}
+
 zoicb_status zoicb_synth_samples(zoicb_ctx* ctx, uint32_t W, uint32_t H, uint32_t spp, uint64_t seed, uint64_t first_index,
                                  uint64_t n, void* d_samples, void* stream) {
     if (!ctx) return api_fail(ZOICB_ERR_INVALID_ARGUMENT, "zoicb_synth_samples: null context");

@@ -93,6 +93,41 @@ differentials_kernel(const __grid_constant__ CameraState cam, const float4* __re
     }
 }
 
+// camera -> world for the differentials: all four are DIFFERENCES of points or directions, so each is multiplied by the
+// 3x3 part of the camera-to-world matrix, with the fma chain zoicb_transform_rays uses for directions:
+//   v'_r = fma(m[r][0], vx, fma(m[r][1], vy, m[r][2] * vz))
+struct DiffXform { float m[12]; };
+__global__ void __launch_bounds__(256)
+transform_diffs_kernel(const __grid_constant__ DiffXform X, const float4* __restrict__ in, uint64_t n, float4* __restrict__ out) {
+    const float* m = X.m;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const float4 a = in[3 * i], b = in[3 * i + 1], c = in[3 * i + 2];
+        const float v[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
+        float w[12];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float x = v[3 * k], y = v[3 * k + 1], z = v[3 * k + 2];
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+                w[3 * k + r] = __fmaf_rn(m[4 * r], x, __fmaf_rn(m[4 * r + 1], y, __fmul_rn(m[4 * r + 2], z)));
+        }
+        out[3 * i] = make_float4(w[0], w[1], w[2], w[3]);
+        out[3 * i + 1] = make_float4(w[4], w[5], w[6], w[7]);
+        out[3 * i + 2] = make_float4(w[8], w[9], w[10], w[11]);
+    }
+}
+
+cudaError_t launch_transform_diffs(const float* m3x4, const float4* in, uint64_t n, float4* out, cudaStream_t st, int* launches) {
+    if (n == 0) return cudaSuccess;
+    DiffXform X;
+    for (int i = 0; i < 12; ++i) X.m[i] = m3x4[i];
+    const uint64_t want = (n + 255) / 256, cap = (uint64_t)sm_count() * 8;
+    transform_diffs_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, st>>>(X, in, n, out);
+    if (launches) *launches += 1;
+    return cudaGetLastError();
+}
+
 cudaError_t launch_differentials(const CameraState& cam, const float4* samples, uint64_t n, uint64_t first_index, uint64_t seed,
                                  float dsx, float dsy, const RayRecord* rays, float4* out, cudaStream_t st, int* launches) {
     if (n == 0) return cudaSuccess;
