@@ -277,7 +277,10 @@ ZOICB_API zoicb_status zoicb_census(zoicb_ctx* ctx, const zoicb_ray* d_fast, con
  * ncclSend / grouped ncclRecv (libnccl.so.2 is resolved at run time; none is needed for FUSED / PUSH).
  * Set-up: create on every rank -> export a blob -> exchange the blobs by any means (torch.distributed, MPI, files) ->
  * connect with all world blobs in rank order.  NCCL transport: instead (or as well) zoicb_gather_init_nccl with an id
- * made by zoicb_nccl_unique_id on one rank, or zoicb_gather_use_nccl_comm with a communicator the caller owns. */
+ * made by zoicb_nccl_unique_id on one rank, or zoicb_gather_use_nccl_comm with a communicator the caller owns.
+ * Failure: the ranks number their rounds without talking, so a gathered zoicb_run_job that returns an error on ANY rank
+ * (a flag wait timed out after ZOICB_GATHER_TIMEOUT_S seconds, 10 by default; a CUDA error) leaves the gather out of
+ * step -- destroy it on every rank and build a new one; the error flag is sticky so later jobs fail fast, not hang. */
 enum { ZOICB_GATHER_FUSED = 1, ZOICB_GATHER_PUSH = 2, ZOICB_GATHER_NCCL = 3 };
 #define ZOICB_GATHER_BLOB_BYTES 192
 #define ZOICB_NCCL_ID_BYTES 128

@@ -414,7 +414,7 @@ zoicb_status zoicb_gather_use_nccl_comm(zoicb_gather* g, void* nccl_comm) {
 zoicb_status zoicb_gather_read(zoicb_gather* g, uint64_t round, int rank, uint64_t offset, uint64_t n, zoicb_ray* h_out) {
     if (!g || (n && !h_out)) return api_fail(ZOICB_ERR_INVALID_ARGUMENT, "zoicb_gather_read: null argument");
     if (!g->is_consumer()) return api_fail(ZOICB_ERR_INVALID_ARGUMENT, "zoicb_gather_read: only the consumer rank holds the round buffers");
-    if (rank < 0 || rank >= g->world || offset + n > g->tile) return api_fail(ZOICB_ERR_INVALID_ARGUMENT, "zoicb_gather_read: out of range");
+    if (rank < 0 || rank >= g->world || offset > g->tile || n > g->tile - offset) return api_fail(ZOICB_ERR_INVALID_ARGUMENT, "zoicb_gather_read: out of range");
     if (!n) return ZOICB_OK;
     ZGUARD(g->device);
     ZCUDA(cudaDeviceSynchronize(), "cudaDeviceSynchronize");
