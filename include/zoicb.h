@@ -337,6 +337,10 @@ ZOICB_API zoicb_status zoicb_debug_sort_orders(const float* values, int32_t n, i
 ZOICB_API zoicb_status zoicb_debug_lut_boxes(int device, const uint32_t* draws, const uint8_t* accept, int32_t n_film,
                                              int32_t per_film, float first_aperture, float* boxes_device, float* boxes_host);
 
+/* Test hook: the float the thin-lens kernels compare qx^2 + qy^2 with instead of taking the root (the smallest s >= 0 whose
+ * correctly rounded square root is >= radius; zoic_b200/csrc/camera_state.h: ov_s_threshold).  Host only. */
+ZOICB_API float zoicb_debug_sqrt_threshold(float radius);
+
 /* Measured fp32 FMA throughput of the device (dependent-chain-free FFMA kernel), in TFLOP/s: the
  * denominator of the fp32 roofline that bench.py reports. */
 ZOICB_API zoicb_status zoicb_measure_fp32_peak(int device, double* tflops);

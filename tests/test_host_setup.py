@@ -260,3 +260,31 @@ def test_bokeh_tables_random_images_with_ties(port):
             assert a.dtype == b.dtype and np.array_equal(a.view(np.uint32) if a.dtype == np.float32 else a,
                                                          b.view(np.uint32) if b.dtype == np.float32 else b), (k, h, w, levels)
         p.close()
+
+
+def test_sqrt_threshold_decides_like_the_rounded_root():
+    """The thin-lens kernels test qx^2 + qy^2 < ov_s_threshold instead of sqrt(qx^2 + qy^2) < radius (reference
+    src/zoic.cpp:1302-1304).  The two agree for EVERY s iff the threshold is the smallest float whose correctly rounded
+    root reaches the radius: checked here at the threshold and its predecessor, and on samples of s around it, with
+    numpy's float32 sqrt (IEEE, like the device's __fsqrt_rn and the reference's sqrtf)."""
+    lib = capi.load()
+    rng = np.random.default_rng(5)
+    radii = np.concatenate([
+        np.float32([1e-30, 1.1754944e-38, 1e-41, 1e-20, 0.5, 1.0, 2.0, 3.0, 1.25, 0.1, 1e10, 1.8446743e19, 1.8446744e19, 3e38]),
+        (rng.random(300, dtype=np.float32) * np.float32(10.0)).astype(np.float32),
+        np.exp(rng.uniform(-80, 80, 300)).astype(np.float32)])
+    with np.errstate(over="ignore", invalid="ignore"):
+        for r in radii:
+            t = np.float32(lib.zoicb_debug_sqrt_threshold(float(r)))
+            assert np.sqrt(t) >= r, (r, t)
+            below = np.nextafter(t, np.float32(0.0))
+            assert t == 0 or np.sqrt(below) < r, (r, t)
+            # a cloud of s values around the threshold: the two forms of the test agree on each
+            bits = t.view(np.uint32).astype(np.int64) + np.arange(-2000, 2001)
+            bits = bits[(bits >= 0) & (bits <= 0x7F800000)]
+            s = bits.astype(np.uint32).view(np.float32)
+            assert np.array_equal(np.sqrt(s) < r, s < t), r
+    # nothing passes a radius that is zero, negative or NaN; every finite s passes an infinite one
+    for r in (0.0, -0.0, -1.0, float("nan")):
+        assert lib.zoicb_debug_sqrt_threshold(r) == 0.0
+    assert lib.zoicb_debug_sqrt_threshold(float("inf")) == float("inf")

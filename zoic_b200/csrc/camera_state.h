@@ -73,6 +73,11 @@ struct ThinState {
     int32_t use_dof;
     int32_t use_ov;         // opticalVignettingDistance > 0
     float ov_guard;         // guarded fast path: |hyp - ov_radius_true| below this => undecided
+    // The reference's test is sqrt(s) < ov_radius_true with s = qx^2 + qy^2 (:1302-1304).  A correctly rounded square root is
+    // monotone, so the s that pass are exactly those below one float: ov_s_threshold = the smallest s >= 0 whose rounded
+    // root is >= ov_radius_true (0 when the radius is <= 0 or NaN, +inf when every finite s passes).  The kernels compare
+    // s < ov_s_threshold -- the same decision for every s (NaN and +inf fail both forms) without the IEEE root.
+    float ov_s_threshold;
 };
 
 // Image-based aperture sampling tables (device pointers), src/zoic.cpp:117-122

@@ -710,6 +710,8 @@ zoicb_status zoicb_debug_lut_boxes(int device, const uint32_t* draws, const uint
     return ZOICB_OK;
 }
 
+float zoicb_debug_sqrt_threshold(float radius) { return sqrt_threshold(radius); }
+
 zoicb_status zoicb_get_create_times(const zoicb_ctx* ctx, double* total_ms, double* lut_ms, double* bokeh_ms) {
     if (!ctx) return api_fail(ZOICB_ERR_INVALID_ARGUMENT, "zoicb_get_create_times: null context");
     if (total_ms) *total_ms = ctx->create_ms;

@@ -452,6 +452,21 @@ zoicb_status build_bokeh(const float* rgb, int w, int h, int nch, HostBokeh* out
 
 }  // namespace
 
+// The smallest float s >= 0 with fl(sqrt(s)) >= r (camera_state.h: ThinState::ov_s_threshold): bisection over the bit patterns
+// of the non-negative floats, which are ordered like their values; the host's sqrtf is the correctly rounded root the
+// device's __fsqrt_rn computes.
+float sqrt_threshold(float r) {
+    if (!(r > 0.0f)) return 0.0f;   // r <= 0 or NaN: no s has a root below r
+    uint32_t lo = 0u, hi = 0x7F800000u;   // invariant: root(lo) < r (root(0) = 0), root(hi) >= r (root(+inf) = +inf)
+    while (hi - lo > 1u) {
+        const uint32_t mid = lo + (hi - lo) / 2u;
+        float m; std::memcpy(&m, &mid, 4);
+        if (sqrtf(m) >= r) hi = mid; else lo = mid;
+    }
+    float out; std::memcpy(&out, &hi, 4);
+    return out;
+}
+
 void lut_fold_boxes_host(const uint32_t* draws, const uint8_t* accept, int n_film, int per_film, float ap, float* boxes) {
     for (int f = 0; f < n_film; ++f) {
         float minx = 0, miny = 0, maxx = 0, maxy = 0;
@@ -539,6 +554,7 @@ zoicb_status build_camera(const zoicb_params& p, const float* rgb, int w, int h,
         T.use_dof = p.useDof ? 1 : 0;
         T.use_ov = p.opticalVignettingDistance > 0.0f ? 1 : 0;
         T.ov_guard = 2e-5f * T.ov_radius_true;
+        T.ov_s_threshold = sqrt_threshold(T.ov_radius_true);
         return ZOICB_OK;
     }
     if (p.lensModel != ZOICB_RAYTRACED) { *err = "lensModel must be THINLENS (0) or RAYTRACED (1)"; return ZOICB_ERR_INVALID_ARGUMENT; }

@@ -44,6 +44,9 @@ typedef int (*LutTraceFn)(void* user, const LensState& lens, const float* film_x
 // the reference's in-order fold of one film position's accepted candidates, re-arm quirk (:1423) included
 void lut_fold_boxes_host(const uint32_t* draws, const uint8_t* accept, int n_film, int per_film, float ap, float* boxes);
 
+// the smallest float s >= 0 whose correctly rounded square root is >= r (0 for r <= 0 or NaN; +inf when r = +inf)
+float sqrt_threshold(float r);
+
 // A callback that builds the image-based aperture tables (all members of HostBokeh) from a validated image.
 // The C-ABI passes the GPU build (bokeh_build.cu); without one the host statement runs
 // (zoicb_setup_host_only, which has no device).

@@ -194,8 +194,8 @@ __device__ __forceinline__ void thin_exact_sample(const CameraState& cam, const 
                 // empericalOpticalVignetting
                 float qx = xsub(xmul(dir.x, T.ov_distance), origin.x);
                 float qy = xsub(xmul(dir.y, T.ov_distance), origin.y);
-                float hyp = xsqrt(xadd(xmul(qx, qx), xmul(qy, qy)));
-                if (fabsf(hyp) < T.ov_radius_true) break;
+                // sqrt(s) < ov_radius_true, decided on s itself (camera_state.h: ov_s_threshold)
+                if (xadd(xmul(qx, qx), xmul(qy, qy)) < T.ov_s_threshold) break;
                 float u, v;
                 draw_pair(rng, &u, &v);
                 lens_sample<kImage>(bk, u, v, &lx, &ly);

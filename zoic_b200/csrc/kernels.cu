@@ -213,8 +213,8 @@ thin_persistent_kernel(const __grid_constant__ CameraState cam, const float4* __
         const Vec3 dir = vnormalize(vsub(focus, origin));
         const float qx = xsub(xmul(dir.x, T.ov_distance), origin.x);
         const float qy = xsub(xmul(dir.y, T.ov_distance), origin.y);
-        const float hyp = xsqrt(xadd(xmul(qx, qx), xmul(qy, qy)));
-        const bool pass = fabsf(hyp) < T.ov_radius_true;
+        // the reference's sqrt(s) < ov_radius_true, decided on s itself (camera_state.h: ov_s_threshold)
+        const bool pass = xadd(xmul(qx, qx), xmul(qy, qy)) < T.ov_s_threshold;
         if (have) {
             ls.attempts++;
             // the reference stops sampling once tries has passed maxtries, whatever the last test said
