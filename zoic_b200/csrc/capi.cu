@@ -146,7 +146,6 @@ cudaError_t zoicb::api_get_workspace(zoicb_ctx* c, cudaStream_t st, uint64_t n, 
     Workspace& w = c->workspaces[st];
     unsigned long long want = n / 24 + 4096;
     if (want > (1ull << 27)) want = 1ull << 27;
-    if (want < kMinWorkspaceRecords) want = kMinWorkspaceRecords;
     cudaError_t e;
     if (!w.counters) {
         if ((e = cudaMalloc(&w.counters, 4 * sizeof(unsigned long long))) != cudaSuccess) return e;

@@ -223,7 +223,7 @@ struct JobBuffers {
             if ((e = cudaMalloc(&exact, cap * sizeof(RayRecord))) != cudaSuccess) return e;
             cap_exact = cap;
         }
-        const uint64_t want = std::max<uint64_t>(cap / 24 + 4096, kMinWorkspaceRecords);   // room for the undecided samples of a tile (capi.cu: api_get_workspace)
+        const uint64_t want = cap / 24 + 4096;   // room for the undecided samples of a tile (capi.cu: api_get_workspace)
         if (want > cap_queue) {
             cudaFree(ws.queue); ws.queue = nullptr; cap_queue = 0;
             if ((e = cudaMalloc(&ws.queue, want * sizeof(QueueRecord))) != cudaSuccess) return e;

@@ -150,9 +150,6 @@ kolb_exact_persistent_kernel(const __grid_constant__ CameraState cam, const floa
 #define ZOICB_THIN_CTAS 6   // resident CTAs of 8 warps per SM: 48 warps at <= 40 registers (4 -> 5 -> 6: 14.7 -> 16.3 -> 17.2 Grays/s on
                            // config 3, profiles/r01b_ab.txt; 8 spills)
 #endif
-#ifndef ZOICB_THIN_PREP_DEFAULT
-#define ZOICB_THIN_PREP_DEFAULT 1
-#endif
 template <bool kImage>
 __global__ void __launch_bounds__(256, ZOICB_THIN_CTAS)
 thin_persistent_kernel(const __grid_constant__ CameraState cam, const float4* __restrict__ samples, uint64_t n,
@@ -232,120 +229,6 @@ thin_persistent_kernel(const __grid_constant__ CameraState cam, const float4* __
             }
         }
     }
-    flush_stats(ls, stats);
-}
-
-// The same kernel with PREPARED BLOCKS.  What a sample costs before its first attempt (pinhole direction, focus point: a
-// root, a reciprocal and a division) and at its first retry (seeding its stream: two 64-bit mixes) is done above by
-// the few lanes that happen to need it in an iteration -- 10.6 and 6 of 32 on config 3, a quarter of the kernel's issue
-// slots.  Here a warp makes 32 consecutive samples ready in ONE dense pass and parks the result (focus point, seeded
-// stream, first lens sample: 40 bytes each) in a private 1280-byte strip of global scratch, which lives in L2 (9 MB for
-// the whole grid, rewritten all the time); a lane that finishes a ray adopts the next parked sample with two loads.
-// The arithmetic per sample is the same, so the records are.  (Registers cannot hold the block -- nine more live
-// registers cost a CTA per SM, profiles/r02_ab.txt call 16 -- and shared memory for it would take 48 KB per SM from the
-// L1 that holds the column tables.)
-constexpr unsigned kPrepWords = 320;   // per warp: 32 x 8 words (focus.xyz, -, stream) + 32 x 2 words (first lens sample)
-template <bool kImage>
-__global__ void __launch_bounds__(256, ZOICB_THIN_CTAS)
-thin_prepared_kernel(const __grid_constant__ CameraState cam, const float4* __restrict__ samples, uint64_t n,
-                     uint64_t first_index, uint64_t seed, RayRecord* __restrict__ rays,
-                     DeviceStats* stats, unsigned long long* chunk_counter, float* scratch) {
-    BokehView bk;
-    if (kImage) bk = stage_bokeh(cam);
-    const ThinState& T = cam.thin;
-    const unsigned lane = threadIdx.x & 31;
-    const unsigned strip = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * kPrepWords;   // word offset of the warp's strip (< 2^32: 2.3 M words)
-    LocalStats ls = {0, 0, 0, 0, 0, 0, 0};
-    // Next sample of the warp's chunk.  Chunks start at multiples of kChunk and blocks at multiples of 32, so `cur` alone
-    // says where the warp stands: at a multiple of 32 (or at n) nothing is parked, at a multiple of kChunk (or at n) the
-    // chunk is used up -- both are left behind at once, since a block is parked and a sample adopted in the same round.
-    uint64_t cur = 0;
-    bool exhausted = false, have = false;
-    uint64_t idx = 0;
-    Vec3 focus = vmake(0.0f, 0.0f, 0.0f);
-    Xor128 rng = {0, 0, 0, 0};
-    int tries = 0;   // -1: adopted, first attempt (its lens sample is the camera sample's own) still to come
-    float ua = 0.0f, ub = 0.0f;
-
-    for (;;) {
-        unsigned need = __ballot_sync(0xffffffffu, !have);
-        while (need) {
-            if ((cur & 31u) == 0u || cur >= n) {
-                if ((cur & (uint64_t)(kChunk - 1)) == 0u || cur >= n) {
-                    if (exhausted) break;
-                    unsigned long long base = 0;
-                    if (lane == 0) base = atomicAdd(chunk_counter, (unsigned long long)kChunk);
-                    base = __shfl_sync(0xffffffffu, base, 0);
-                    if (base >= n) { exhausted = true; break; }
-                    cur = base;
-                }
-                __syncwarp();   // every lane has read what it adopted from the previous block
-                const uint64_t j = cur + lane;
-                if (j < n) {   // a block never crosses its chunk's end: that is a multiple of 32, or n
-                    const float4 s = __ldcs(samples + j);
-                    if (j + 32 < n) asm volatile("prefetch.global.L2 [%0];" ::"l"(samples + j + 32));   // the next block's, on its way
-                    const Vec3 dir0 = vnormalize(vmake(xmul(s.x, T.tan_fov), xmul(s.y, T.tan_fov), 1.0f));
-                    const Vec3 f = vscale(dir0, fabsf(xdiv(T.focal_distance, dir0.z)));
-                    const Xor128 r = sample_stream(seed, first_index + j);
-                    asm volatile("st.global.cg.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(scratch + (strip + lane * 8)),
-                                 "r"(__float_as_uint(f.x)), "r"(__float_as_uint(f.y)), "r"(__float_as_uint(f.z)), "r"(0u),
-                                 "r"(r.x), "r"(r.y), "r"(r.z), "r"(r.w) : "memory");
-                    asm volatile("st.global.cg.v2.f32 [%0], {%1,%2};" ::"l"(scratch + (strip + 256 + lane * 2)), "f"(s.z), "f"(s.w) : "memory");
-                }
-                __syncwarp();   // orders the block's stores before the other lanes' loads
-            }
-            const uint64_t left = n - cur;
-            const unsigned in_block = 32u - ((unsigned)cur & 31u);
-            const unsigned avail = left < in_block ? (unsigned)left : in_block;
-            const unsigned want = __popc(need);
-            const unsigned take = want < avail ? want : avail;
-            unsigned lt_mask;   // read where it is used: two live registers less than carrying it and the lane through the attempt
-            asm volatile("mov.u32 %0, %%lanemask_lt;" : "=r"(lt_mask));
-            const unsigned rank = __popc(need & lt_mask);
-            if (!have && rank < take) {
-                idx = cur + rank;
-                const unsigned e = (unsigned)idx & 31u;
-                unsigned f0, f1, f2, f3;
-                asm volatile("ld.global.cg.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                             : "=r"(f0), "=r"(f1), "=r"(f2), "=r"(f3), "=r"(rng.x), "=r"(rng.y), "=r"(rng.z), "=r"(rng.w)
-                             : "l"(scratch + (strip + e * 8)) : "memory");
-                asm volatile("ld.global.cg.v2.f32 {%0,%1}, [%2];" : "=f"(ua), "=f"(ub) : "l"(scratch + (strip + 256 + e * 2)) : "memory");
-                focus = vmake(__uint_as_float(f0), __uint_as_float(f1), __uint_as_float(f2));
-                (void)f3;
-                tries = -1;
-                have = true;
-            }
-            cur += take;
-            need = __ballot_sync(0xffffffffu, !have);
-        }
-        if (!__any_sync(0xffffffffu, have)) {
-            if (exhausted) break;
-            continue;
-        }
-        if (have) {
-            if (tries >= 0) draw_pair(rng, &ua, &ub);
-            ++tries;
-        }
-        float lx, ly;
-        lens_sample<kImage>(bk, ua, ub, &lx, &ly);
-        const Vec3 origin = vmake(xmul(lx, T.aperture_radius), xmul(ly, T.aperture_radius), 0.0f);
-        const Vec3 dir = vnormalize(vsub(focus, origin));
-        const float qx = xsub(xmul(dir.x, T.ov_distance), origin.x);
-        const float qy = xsub(xmul(dir.y, T.ov_distance), origin.y);
-        const bool pass = xadd(xmul(qx, qx), xmul(qy, qy)) < T.ov_s_threshold;   // camera_state.h: ov_s_threshold
-        if (have) {
-            ls.attempts++;
-            if (pass || tries > kMaxTries) {
-                float weight = 1.0f;
-                if (tries > kMaxTries) { weight = 0.0f; ls.vignetted++; }
-                else ls.success++;
-                weight = xmul(weight, cam.weight_scale);
-                store_ray(rays, idx, make_float4(origin.x, origin.y, origin.z, weight), make_float4(dir.x, dir.y, -dir.z, (float)tries));
-                have = false;
-            }
-        }
-    }
-    ls.rays = ls.success + ls.vignetted;
     flush_stats(ls, stats);
 }
 
@@ -651,18 +534,10 @@ static cudaError_t launch_variant(const CameraState& cam, int mode, const float4
             if (carve >= 0) pct = carve;
             cudaFuncSetAttribute(thin_persistent_kernel<kImage>, cudaFuncAttributePreferredSharedMemoryCarveout, pct > 100 ? 100 : pct);
         }
-        // prepared blocks (thin_prepared_kernel): ZOICB_THIN_PREP=0/1 overrides the default (A/B)
-        static const int prep = [] { const char* v = getenv("ZOICB_THIN_PREP"); return v ? atoi(v) : ZOICB_THIN_PREP_DEFAULT; }();
+        // (prepared blocks -- 32 samples made ready by one dense pass and parked in registers (call 16) or in L2 scratch
+        // (call 21) for finished lanes to adopt -- save 6-12 % of the warp instructions, stay bit-exact and lose to the
+        // registers / the L2 round trip they cost: profiles/r02_ab.txt)
         const unsigned grid = (unsigned)sm_count() * ZOICB_THIN_CTAS;
-        const unsigned long long strip_words = (unsigned long long)grid * (threads / 32) * kPrepWords;   // 4-byte words
-        if (prep && ws.queue && ws.capacity * (sizeof(QueueRecord) / 4) >= strip_words) {
-            if (kImage) cudaFuncSetAttribute(thin_prepared_kernel<kImage>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                             carve >= 0 ? (carve > 100 ? 100 : carve) : (int)(((size_t)ZOICB_THIN_CTAS * (smem + 2200) * 100 + 233471) / 233472));
-            thin_prepared_kernel<kImage><<<grid, threads, smem, st>>>(cam, samples, n, first_index, seed, rays, stats, ws.counters,
-                                                                      reinterpret_cast<float*>(ws.queue));
-            if (launches) *launches += 1;
-            return cudaGetLastError();
-        }
         thin_persistent_kernel<kImage><<<grid, threads, smem, st>>>(cam, samples, n, first_index, seed, rays,
                                                                                       stats, stage, ws.counters);
         if (launches) *launches += 1;

@@ -26,9 +26,7 @@ __host__ __device__ inline unsigned queue_visits(QueueRecord q) { return (unsign
 
 // Per-stream scratch: counters[0] = chunk cursor of the main kernel, counters[1] = number of queued (undecided)
 // samples, counters[2] = work cursor of the exact persistent kernel, counters[3] spare;
-// queue[capacity] = the undecided samples of the raytraced kernels; the thin-lens retry kernel parks its prepared blocks
-// there instead (kernels.cu: thin_prepared_kernel, 1280 bytes per resident warp), hence the minimum size.
-constexpr unsigned long long kMinWorkspaceRecords = 1ull << 21;   // 16 MB
+// queue[capacity] = the undecided samples.
 struct Workspace {
     unsigned long long* counters;
     QueueRecord* queue;
