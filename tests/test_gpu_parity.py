@@ -249,6 +249,12 @@ def test_guarded_thin_lens_is_bit_exact(port):
     for image, kw in [(None, dict(lensModel=0, focalLength=3.5, fStop=2.8, opticalVignettingDistance=2.0)),
                       (hex_bokeh_image(255), dict(lensModel=0, focalLength=3.5, fStop=2.8, useImage=1,
                                                   opticalVignettingDistance=2.0, exposureControl=-0.5)),
+                      # 255 columns and fewer get byte-wide column tables (camera_state.h: BokehCompact), wider images the
+                      # 16-bit ones; 255 x 120: rows and columns differ, 301: the wide path
+                      (hex_bokeh_image(255)[:120].copy(), dict(lensModel=0, focalLength=3.5, fStop=2.0, useImage=1,
+                                                               opticalVignettingDistance=3.0)),
+                      (hex_bokeh_image(301), dict(lensModel=0, focalLength=3.5, fStop=2.8, useImage=1,
+                                                  opticalVignettingDistance=2.0)),
                       (None, dict(lensModel=0, focalLength=2.0, fStop=1.4, opticalVignettingDistance=4.0,
                                   opticalVignettingRadius=0.6))]:   # harsh vignetting: many zero-weight rays
         cam = ZoicCamera(image=image, **kw)

@@ -102,6 +102,16 @@ struct BokehTables {
     int32_t row_shift, col_shift;   // log2 of the guide resolutions
 };
 
+// Byte-wide copies of the two big 16-bit column tables, for images of at most 255 columns (every entry is a column
+// number or a column count, <= w): the thin-lens retry kernel is bound by the latency of its table loads, and the
+// working set of config 3 (column CDF 167 KB + guide 262 KB + pixel indices 84 KB) is more than twice the L1 it runs in;
+// the narrow copies take 197 KB off it.  Null when absent (wider images, the raytraced model).
+struct BokehCompact {
+    const uint8_t* col_guide8;    // [h * (2^col_shift + 2)]
+    const uint8_t* rel_column8;   // [h*w]
+};
+constexpr int kCompactMaxWidth = 255, kCompactMaxRows = 512;   // rows: the kernel also stages a third row table (kernels.cu)
+
 struct CameraState {
     int32_t lens_model;  // 0 thin lens, 1 raytraced
     int32_t use_image;
@@ -110,6 +120,7 @@ struct CameraState {
     ThinState thin;
     BokehTables bokeh;
     LensState lens;
+    BokehCompact compact;
 };
 
 // per-launch counters, accumulated with one atomicAdd per block per counter

@@ -172,7 +172,7 @@ void free_ctx(zoicb_ctx* c) {
     if (c->job_cache && c->job_cache_free) c->job_cache_free(c->job_cache);
     for (auto& kv : c->workspaces) { cudaFree(kv.second.counters); cudaFree(kv.second.queue); }
     cudaFree(c->d_cdf_row); cudaFree(c->d_row_idx); cudaFree(c->d_cdf_col); cudaFree(c->d_rel_col);
-    cudaFree(c->d_row_guide); cudaFree(c->d_col_guide); cudaFree(c->d_dxy);
+    cudaFree(c->d_row_guide); cudaFree(c->d_col_guide); cudaFree(c->d_dxy); cudaFree(c->d_compact);
     cudaFree(c->d_stats);
     for (int s = 0; s < zoicb_ctx::kSlots; ++s) {
         if (c->streams[s]) cudaStreamDestroy(c->streams[s]);
@@ -234,6 +234,18 @@ zoicb_status zoicb_create(const zoicb_params* params, const float* rgb, int widt
         bt.row_guide = c->d_row_guide; bt.col_guide = c->d_col_guide;
         bt.dx_of_col = c->d_dxy; bt.dy_of_row = c->d_dxy + hb.w;
         bt.w = hb.w; bt.h = hb.h; bt.row_shift = hb.row_shift; bt.col_shift = hb.col_shift;
+        if (params->lensModel == ZOICB_THINLENS && hb.w <= kCompactMaxWidth && hb.h <= kCompactMaxRows) {
+            // byte-wide copies of the two big column tables for the thin-lens retry kernel (camera_state.h: BokehCompact)
+            const size_t ng = hb.col_guide.size(), np = (size_t)hb.w * hb.h;
+            std::vector<uint8_t> narrow(ng + np);
+            for (size_t i = 0; i < ng; ++i) narrow[i] = (uint8_t)hb.col_guide[i];
+            for (int r = 0; r < hb.h; ++r)
+                for (int k = 0; k < hb.w; ++k) narrow[ng + (size_t)r * hb.w + k] = (uint8_t)(hb.column_indices[(size_t)r * hb.w + k] - r * hb.w);
+            if ((e = cudaMalloc(&c->d_compact, narrow.size())) != cudaSuccess) return bail(e, "cudaMalloc(bokeh)");
+            if ((e = cudaMemcpy(c->d_compact, narrow.data(), narrow.size(), cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e, "cudaMemcpy(bokeh)");
+            c->host.state.compact.col_guide8 = c->d_compact;
+            c->host.state.compact.rel_column8 = c->d_compact + ng;
+        }
     } else if (hb.degenerate) {
         // An image the reference accepts but treats as invalid (fewer than 3 channels, src/zoic.cpp:135-137): every
         // bokehSample answers the lens centre (0, 0) (:420-425).  The kernels keep their one code path: a 1 x 1 table whose

@@ -24,6 +24,7 @@ struct zoicb_ctx {
     uint16_t* d_row_guide = nullptr;
     uint16_t* d_col_guide = nullptr;
     float* d_dxy = nullptr;   // dx_of_col[w] then dy_of_row[h]
+    uint8_t* d_compact = nullptr;   // byte-wide column guide, then byte-wide pixel indices (camera_state.h: BokehCompact)
     zoicb::DeviceStats* d_stats = nullptr;
     // guarded-mode scratch, one per stream the caller uses (stream order serialises reuse).  gen_mu is held from the
     // workspace lookup to the last launch of a generate call, so two host threads driving the same context cannot

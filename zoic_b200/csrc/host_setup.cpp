@@ -506,6 +506,8 @@ zoicb_status build_camera(const zoicb_params& p, const float* rgb, int w, int h,
     CameraState& S = out->state;
     zoicb_constants& C = out->constants;
     S.lens_model = p.lensModel;
+    S.compact.col_guide8 = nullptr;   // filled in by the C-ABI for narrow images (camera_state.h: BokehCompact)
+    S.compact.rel_column8 = nullptr;
     S.use_image = p.useImage ? 1 : 0;
     const float e2 = xmul(p.exposureControl, p.exposureControl);  // :1981-1987
     S.weight_scale = 1.0f;

@@ -41,8 +41,9 @@ __device__ __forceinline__ void store_ray(RayRecord* __restrict__ rays, uint64_t
 // (whole range) take the libstdc++ first/len halving with a warp-uniform number of rounds and predicated updates: no
 // lane leaves the loop early.  (With a data-dependent trip count ptxas 12.9 let the early lanes run ahead and re-use the
 // uniform registers that hold the table pointers while the late lanes were still reading them.)
-template <typename Load, typename Guide>
-__device__ __forceinline__ int upper_bound_guided(int n, int shift, float u, Load load, Guide guide) {
+// `last()` = the table's final entry, load(n - 1), for callers that have it somewhere cheaper
+template <typename Load, typename Guide, typename Last>
+__device__ __forceinline__ int upper_bound_guided(int n, int shift, float u, Load load, Guide guide, Last last) {
     int first = 0, len = n;
     bool past = false;
     if (u >= 0.0f) {
@@ -51,7 +52,7 @@ __device__ __forceinline__ int upper_bound_guided(int n, int shift, float u, Loa
         const int k = f >= (float)G ? G : (int)f;
         first = guide(k);
         len = guide(k + 1) - first;
-        past = u >= load(n - 1);   // false for a NaN table (black image): its guides all hold n
+        past = u >= last();   // false for a NaN table (black image): its guides all hold n
     }
     const int maxlen = (int)__reduce_max_sync(__activemask(), (unsigned)len);
     constexpr int kCount = ZOICB_BOKEH_COUNT;
@@ -77,6 +78,11 @@ __device__ __forceinline__ int upper_bound_guided(int n, int shift, float u, Loa
     return past ? n : first;
 }
 
+template <typename Load, typename Guide>
+__device__ __forceinline__ int upper_bound_guided(int n, int shift, float u, Load load, Guide guide) {
+    return upper_bound_guided(n, shift, u, load, guide, [&]() { return load(n - 1); });
+}
+
 // The row tables (cdfRow, rowIndices: 8 bytes per image row) are always staged in dynamic shared memory --
 // s_rows[0..h) holds the CDF, s_rows[h..2h) the row indices -- and addressed as shared memory (no generic
 // pointers); the per-row column tables stay in global memory (L1/L2 resident).
@@ -93,27 +99,42 @@ struct BokehView {
     const float* dy_of_row;
     int w, h;
     int row_shift, col_shift;
+    const uint8_t* col_guide8;   // camera_state.h: BokehCompact (kCompact callers only)
+    const uint8_t* rel_col8;
 };
 
+// kCompact: the byte-wide column tables (BokehCompact) and the rows' final CDF values from shared memory,
+// s_rows[2h + actual row] (staged by the caller, stage_row_finals): the same values from smaller / nearer places.
+template <bool kCompact = false>
 __device__ __forceinline__ void bokeh_sample(const BokehView& b, float u_row, float u_col, float* dx, float* dy) {
     int r = upper_bound_guided(b.h, b.row_shift, u_row, [&](int i) { return s_rows[i]; }, [&](int k) { return (int)__ldg(b.row_guide + k); });
     if (r >= b.h) r = b.h - 1;
     const int row = __float_as_int(s_rows[b.h + r]);
     const int start = row * b.w;
     const float* __restrict__ col = b.cdf_col + start;
-    const uint16_t* __restrict__ cg = b.col_guide + row * ((1 << b.col_shift) + 2);
-    int c = upper_bound_guided(b.w, b.col_shift, u_col, [&](int i) { return __ldg(col + i); }, [&](int k) { return (int)__ldg(cg + k); });
-    if (c >= b.w) c = b.w - 1;
-    const int rel = (int)__ldg(b.rel_col + start + c);
+    const int goff = row * ((1 << b.col_shift) + 2);
+    int c, rel;
+    if (kCompact) {
+        const uint8_t* __restrict__ cg = b.col_guide8 + goff;
+        c = upper_bound_guided(b.w, b.col_shift, u_col, [&](int i) { return __ldg(col + i); }, [&](int k) { return (int)__ldg(cg + k); },
+                               [&]() { return s_rows[2 * b.h + row]; });
+        if (c >= b.w) c = b.w - 1;
+        rel = (int)__ldg(b.rel_col8 + start + c);
+    } else {
+        const uint16_t* __restrict__ cg = b.col_guide + goff;
+        c = upper_bound_guided(b.w, b.col_shift, u_col, [&](int i) { return __ldg(col + i); }, [&](int k) { return (int)__ldg(cg + k); });
+        if (c >= b.w) c = b.w - 1;
+        rel = (int)__ldg(b.rel_col + start + c);
+    }
     // the reference centres the row with the WIDTH (:441) and the column with the HEIGHT (:466) and divides (:479-484):
     // both divisions depend on the column / the row only and are tabulated once per camera with the same operations
     *dx = __ldg(b.dx_of_col + rel);
     *dy = __ldg(b.dy_of_row + row);
 }
 
-template <bool kImage>
+template <bool kImage, bool kCompact = false>
 __device__ __forceinline__ void lens_sample(const BokehView& b, float u, float v, float* lx, float* ly) {
-    if (kImage) bokeh_sample(b, u, v, lx, ly);
+    if (kImage) bokeh_sample<kCompact>(b, u, v, lx, ly);
     else concentric_disk(u, v, lx, ly);
 }
 
@@ -136,12 +157,21 @@ __device__ __forceinline__ BokehView stage_bokeh(const CameraState& cam) {
     b.dx_of_col = cam.bokeh.dx_of_col;
     b.dy_of_row = cam.bokeh.dy_of_row;
     b.row_shift = cam.bokeh.row_shift; b.col_shift = cam.bokeh.col_shift;
+    b.col_guide8 = cam.compact.col_guide8;
+    b.rel_col8 = cam.compact.rel_column8;
     for (int i = threadIdx.x; i < b.h; i += blockDim.x) {
         s_rows[i] = cam.bokeh.cdf_row[i];
         s_rows[b.h + i] = __int_as_float(cam.bokeh.row_indices[i]);
     }
     __syncthreads();
     return b;
+}
+// third row table of the kCompact callers: the final value of every row's column CDF, by actual row (the dynamic shared
+// memory must hold 12 bytes per row then: bokeh_smem_bytes(h) + 4 h)
+__device__ __forceinline__ void stage_row_finals(const CameraState& cam) {
+    const int w = cam.bokeh.w, h = cam.bokeh.h;
+    for (int i = threadIdx.x; i < h; i += blockDim.x) s_rows[2 * h + i] = cam.bokeh.cdf_column[(size_t)i * w + (w - 1)];
+    __syncthreads();
 }
 
 // ------------------------------------------------------------------------------------------------

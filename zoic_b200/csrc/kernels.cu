@@ -150,13 +150,15 @@ kolb_exact_persistent_kernel(const __grid_constant__ CameraState cam, const floa
 #define ZOICB_THIN_CTAS 6   // resident CTAs of 8 warps per SM: 48 warps at <= 40 registers (4 -> 5 -> 6: 14.7 -> 16.3 -> 17.2 Grays/s on
                            // config 3, profiles/r01b_ab.txt; 8 spills)
 #endif
-template <bool kImage>
+// kCompact: byte-wide column tables and the rows' final CDF values in shared memory (camera_state.h: BokehCompact)
+template <bool kImage, bool kCompact>
 __global__ void __launch_bounds__(256, ZOICB_THIN_CTAS)
 thin_persistent_kernel(const __grid_constant__ CameraState cam, const float4* __restrict__ samples, uint64_t n,
                        uint64_t first_index, uint64_t seed, RayRecord* __restrict__ rays,
                        DeviceStats* stats, int stage_rows, unsigned long long* chunk_counter) {
     BokehView bk;
     if (kImage) bk = stage_bokeh(cam);
+    if (kImage && kCompact) stage_row_finals(cam);
     (void)stage_rows;
     const ThinState& T = cam.thin;
     const unsigned lane = threadIdx.x & 31;
@@ -208,7 +210,7 @@ thin_persistent_kernel(const __grid_constant__ CameraState cam, const float4* __
         }
         fresh = false;
         float lx, ly;
-        lens_sample<kImage>(bk, ua, ub, &lx, &ly);
+        lens_sample<kImage, kCompact>(bk, ua, ub, &lx, &ly);
         const Vec3 origin = vmake(xmul(lx, T.aperture_radius), xmul(ly, T.aperture_radius), 0.0f);
         const Vec3 dir = vnormalize(vsub(focus, origin));
         const float qx = xsub(xmul(dir.x, T.ov_distance), origin.x);
@@ -528,18 +530,28 @@ static cudaError_t launch_variant(const CameraState& cam, int mode, const float4
         // the column tables of an image-shaped aperture live in L1 / L2: ask for the smallest shared-memory carve-out that
         // still holds the resident CTAs' row tables, so that L1 gets the rest of the 256 KB
         static const int carve = [] { const char* v = getenv("ZOICB_THIN_CARVEOUT"); return v ? atoi(v) : -1; }();
-        if (kImage) {
-            const size_t need = (size_t)ZOICB_THIN_CTAS * (smem + 2200);
-            int pct = (int)((need * 100 + 233471) / 233472);
-            if (carve >= 0) pct = carve;
-            cudaFuncSetAttribute(thin_persistent_kernel<kImage>, cudaFuncAttributePreferredSharedMemoryCarveout, pct > 100 ? 100 : pct);
-        }
+        // byte-wide column tables when the camera has them (ZOICB_THIN_COMPACT=0 turns them off: A/B)
+        static const bool allow_compact = [] { const char* v = getenv("ZOICB_THIN_COMPACT"); return !v || atoi(v) != 0; }();
+        const bool compact = kImage && allow_compact && cam.compact.col_guide8 && cam.compact.rel_column8;
+        const size_t smem_k = compact ? (((size_t)cam.bokeh.h * 12u + 15u) & ~(size_t)15u) : smem;
+        const size_t need = (size_t)ZOICB_THIN_CTAS * (smem_k + 2200);
+        int pct = (int)((need * 100 + 233471) / 233472);
+        if (carve >= 0) pct = carve;
+        if (pct > 100) pct = 100;
         // (prepared blocks -- 32 samples made ready by one dense pass and parked in registers (call 16) or in L2 scratch
         // (call 21) for finished lanes to adopt -- save 6-12 % of the warp instructions, stay bit-exact and lose to the
         // registers / the L2 round trip they cost: profiles/r02_ab.txt)
         const unsigned grid = (unsigned)sm_count() * ZOICB_THIN_CTAS;
-        thin_persistent_kernel<kImage><<<grid, threads, smem, st>>>(cam, samples, n, first_index, seed, rays,
-                                                                                      stats, stage, ws.counters);
+        if constexpr (kImage) {
+            if (compact) {
+                cudaFuncSetAttribute(thin_persistent_kernel<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+                thin_persistent_kernel<true, true><<<grid, threads, smem_k, st>>>(cam, samples, n, first_index, seed, rays, stats, stage, ws.counters);
+                if (launches) *launches += 1;
+                return cudaGetLastError();
+            }
+            cudaFuncSetAttribute(thin_persistent_kernel<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+        }
+        thin_persistent_kernel<kImage, false><<<grid, threads, smem_k, st>>>(cam, samples, n, first_index, seed, rays, stats, stage, ws.counters);
         if (launches) *launches += 1;
         return cudaGetLastError();
     }
