@@ -88,6 +88,10 @@ __device__ __forceinline__ int upper_bound_guided(int n, int shift, float u, Loa
 // pointers); the per-row column tables stay in global memory (L1/L2 resident).
 extern __shared__ float s_rows[];
 
+#ifndef ZOICB_THIN_SPECULATE
+#define ZOICB_THIN_SPECULATE 1
+#endif
+
 __host__ __device__ inline unsigned bokeh_smem_bytes(int h) { return ((unsigned)h * 8u + 15u) & ~15u; }
 
 struct BokehView {
@@ -116,10 +120,44 @@ __device__ __forceinline__ void bokeh_sample(const BokehView& b, float u_row, fl
     int c, rel;
     if (kCompact) {
         const uint8_t* __restrict__ cg = b.col_guide8 + goff;
-        c = upper_bound_guided(b.w, b.col_shift, u_col, [&](int i) { return __ldg(col + i); }, [&](int k) { return (int)__ldg(cg + k); },
-                               [&]() { return s_rows[2 * b.h + row]; });
-        if (c >= b.w) c = b.w - 1;
-        rel = (int)__ldg(b.rel_col8 + start + c);
+        const uint8_t* __restrict__ rl = b.rel_col8 + start;
+#if ZOICB_THIN_SPECULATE
+        // The chain guide -> CDF entries -> pixel index -> lens coordinate is four dependent loads, and the kernel waits
+        // on them (long scoreboard is its first stall).  With brackets of at most two entries (the usual case at
+        // G >= 2 w) the answer is one of first, first + 1, first + 2: their pixel indices are loaded NEXT TO the CDF
+        // entries instead of after them, and the count picks one.  Same search result (upper_bound_guided's counting
+        // branch, spelled out); every other case -- longer brackets, u < 0 or NaN in any lane -- takes the general path.
+        int first = 0, len = b.w;
+        bool past = false;
+        if (u_col >= 0.0f) {
+            const int G = 1 << b.col_shift;
+            const float f = u_col * (float)G;   // exact: G is a power of two
+            const int k = f >= (float)G ? G : (int)f;
+            first = (int)__ldg(cg + k);
+            len = (int)__ldg(cg + k + 1) - first;
+            past = u_col >= s_rows[2 * b.h + row];
+        }
+        const int maxlen = (int)__reduce_max_sync(__activemask(), (unsigned)len);
+        if (maxlen <= 2) {
+            const int w1 = b.w - 1;
+            const int r0 = (int)__ldg(rl + min(first, w1)), r1 = (int)__ldg(rl + min(first + 1, w1));
+            int cnt = 0;
+            if (0 < len) cnt += (u_col < __ldg(col + first)) ? 0 : 1;
+            rel = cnt == 0 ? r0 : r1;
+            if (maxlen == 2) {   // warp-uniform
+                const int r2 = (int)__ldg(rl + min(first + 2, w1));
+                if (1 < len) cnt += (u_col < __ldg(col + first + 1)) ? 0 : 1;
+                rel = cnt == 2 ? r2 : rel;
+            }
+            if (past) rel = (int)__ldg(rl + w1);   // upper_bound = n, clamped to the last entry
+        } else
+#endif
+        {
+            c = upper_bound_guided(b.w, b.col_shift, u_col, [&](int i) { return __ldg(col + i); }, [&](int k) { return (int)__ldg(cg + k); },
+                                   [&]() { return s_rows[2 * b.h + row]; });
+            if (c >= b.w) c = b.w - 1;
+            rel = (int)__ldg(rl + c);
+        }
     } else {
         const uint16_t* __restrict__ cg = b.col_guide + goff;
         c = upper_bound_guided(b.w, b.col_shift, u_col, [&](int i) { return __ldg(col + i); }, [&](int k) { return (int)__ldg(cg + k); });
