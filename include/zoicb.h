@@ -341,6 +341,12 @@ ZOICB_API zoicb_status zoicb_debug_lut_boxes(int device, const uint32_t* draws, 
  * correctly rounded square root is >= radius; zoic_b200/csrc/camera_state.h: ov_s_threshold).  Host only. */
 ZOICB_API float zoicb_debug_sqrt_threshold(float radius);
 
+/* Test hook: the thin-lens kernel's merged 1 / sqrt(x) (one range check around the fast paths of the IEEE root and the
+ * IEEE reciprocal, zoic_b200/csrc/lens_math.cuh: normalize_factor) against the two library operations, for EVERY float
+ * bit pattern x, on the device.  *mismatches = number of x whose results differ in any bit (NaN = NaN), *first_bad = the
+ * smallest such pattern (0xFFFFFFFF when there is none). */
+ZOICB_API zoicb_status zoicb_debug_check_normalize_factor(int device, uint64_t* mismatches, uint32_t* first_bad);
+
 /* Measured fp32 FMA throughput of the device (dependent-chain-free FFMA kernel), in TFLOP/s: the
  * denominator of the fp32 roofline that bench.py reports. */
 ZOICB_API zoicb_status zoicb_measure_fp32_peak(int device, double* tflops);

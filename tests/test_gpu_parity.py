@@ -241,6 +241,18 @@ def test_guarded_kolb_no_lut_and_bokeh(port):
                         useImage=1, exposureControl=0.3), port, n=100_000, image=hex_bokeh_image(255))
 
 
+def test_merged_normalisation_equals_the_ieee_operations_for_every_float():
+    """The thin-lens retry kernel normalises with one range check around the fast paths of the IEEE root and the IEEE
+    reciprocal (lens_math.cuh: normalize_factor).  The device compares it with __frcp_rn(__fsqrt_rn(x)) -- the reference's
+    1 / sqrtf(x) in AiV3Normalize -- for all 2^32 bit patterns."""
+    import ctypes
+    from zoic_b200 import capi
+    bad, first = ctypes.c_uint64(123), ctypes.c_uint32(0)
+    capi.check(capi.load().zoicb_debug_check_normalize_factor(0, ctypes.byref(bad), ctypes.byref(first)))
+    assert bad.value == 0, "first differing bit pattern: 0x%08x" % first.value
+    assert first.value == 0xFFFFFFFF
+
+
 def test_guarded_thin_lens_is_bit_exact(port):
     """The thin lens has no double-precision step, so its default (persistent-warp) kernel keeps the exact
     arithmetic: bit-identical to the oracle, only the order of work differs."""

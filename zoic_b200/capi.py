@@ -102,6 +102,7 @@ SYMBOLS = {
     "zoicb_debug_sort_orders": (C.c_int, [_P, C.c_int32, _P, _P]),
     "zoicb_measure_fp32_peak": (C.c_int, [C.c_int, C.POINTER(C.c_double)]),
     "zoicb_get_create_times": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "zoicb_debug_check_normalize_factor": (C.c_int, [C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]),
     "zoicb_debug_sqrt_threshold": (C.c_float, [C.c_float]),
     "zoicb_debug_lut_boxes": (C.c_int, [C.c_int, _P, _P, C.c_int32, C.c_int32, C.c_float, _P, _P]),
     "zoicb_run_job": (C.c_int, [_P, C.POINTER(Job), C.POINTER(JobResult)]),

@@ -732,6 +732,25 @@ zoicb_status zoicb_get_create_times(const zoicb_ctx* ctx, double* total_ms, doub
     return ZOICB_OK;
 }
 
+zoicb_status zoicb_debug_check_normalize_factor(int device, uint64_t* mismatches, uint32_t* first_bad) {
+    if (!mismatches || !first_bad) return api_fail(ZOICB_ERR_INVALID_ARGUMENT, "zoicb_debug_check_normalize_factor: null argument");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
+        cudaGetLastError();
+        return api_fail(ZOICB_ERR_CUDA, "zoicb_debug_check_normalize_factor: no such CUDA device (libzoicb has no CPU fallback)");
+    }
+    ZGUARD(device);
+    unsigned long long bad = 0;
+    unsigned first = 0;
+    int launches = 0;
+    const cudaError_t e = check_normalize_factor(&bad, &first, &launches);
+    api_count_launches(launches);
+    if (e != cudaSuccess) return api_cuda_fail(e, "zoicb_debug_check_normalize_factor");
+    *mismatches = bad;
+    *first_bad = first;
+    return ZOICB_OK;
+}
+
 zoicb_status zoicb_measure_fp32_peak(int device, double* tflops) {
     if (!tflops) return api_fail(ZOICB_ERR_INVALID_ARGUMENT, "zoicb_measure_fp32_peak: null argument");
     ZGUARD(device);

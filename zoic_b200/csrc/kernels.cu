@@ -150,6 +150,14 @@ kolb_exact_persistent_kernel(const __grid_constant__ CameraState cam, const floa
 #define ZOICB_THIN_CTAS 6   // resident CTAs of 8 warps per SM: 48 warps at <= 40 registers (4 -> 5 -> 6: 14.7 -> 16.3 -> 17.2 Grays/s on
                            // config 3, profiles/r01b_ab.txt; 8 spills)
 #endif
+#ifndef ZOICB_THIN_MERGED_NORM
+#define ZOICB_THIN_MERGED_NORM 1
+#endif
+#if ZOICB_THIN_MERGED_NORM
+#define ZOICB_THIN_NORMALIZE vnormalize_merged   // lens_math.cuh: same floats, one range check instead of three branches
+#else
+#define ZOICB_THIN_NORMALIZE vnormalize
+#endif
 // kCompact: byte-wide column tables and the rows' final CDF values in shared memory (camera_state.h: BokehCompact)
 template <bool kImage, bool kCompact>
 __global__ void __launch_bounds__(256, ZOICB_THIN_CTAS)
@@ -189,7 +197,7 @@ thin_persistent_kernel(const __grid_constant__ CameraState cam, const float4* __
             if (!have && rank < take) {
                 idx = cur + rank;
                 const float4 s = __ldcs(samples + idx);
-                const Vec3 dir0 = vnormalize(vmake(xmul(s.x, T.tan_fov), xmul(s.y, T.tan_fov), 1.0f));
+                const Vec3 dir0 = ZOICB_THIN_NORMALIZE(vmake(xmul(s.x, T.tan_fov), xmul(s.y, T.tan_fov), 1.0f));
                 focus = vscale(dir0, fabsf(xdiv(T.focal_distance, dir0.z)));
                 ua = s.z;
                 ub = s.w;
@@ -212,7 +220,7 @@ thin_persistent_kernel(const __grid_constant__ CameraState cam, const float4* __
         float lx, ly;
         lens_sample<kImage, kCompact>(bk, ua, ub, &lx, &ly);
         const Vec3 origin = vmake(xmul(lx, T.aperture_radius), xmul(ly, T.aperture_radius), 0.0f);
-        const Vec3 dir = vnormalize(vsub(focus, origin));
+        const Vec3 dir = ZOICB_THIN_NORMALIZE(vsub(focus, origin));
         const float qx = xsub(xmul(dir.x, T.ov_distance), origin.x);
         const float qy = xsub(xmul(dir.y, T.ov_distance), origin.y);
         // the reference's sqrt(s) < ov_radius_true, decided on s itself (camera_state.h: ov_s_threshold)
@@ -642,6 +650,41 @@ cudaError_t launch_lut_bbox(const uint32_t* d_draws, const uint8_t* d_accept, in
     lut_bbox_kernel<<<n_film, 32, 0, st>>>(d_draws, d_accept, per_film, ap, d_boxes);
     if (launches) *launches += 1;
     return cudaGetLastError();
+}
+
+// every float bit pattern: normalize_factor against the library sequence it replaces
+__global__ void __launch_bounds__(256) check_normalize_factor_kernel(unsigned long long* mismatches, unsigned* first_bad) {
+    unsigned long long bad = 0;
+    for (unsigned long long b = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; b < (1ull << 32);
+         b += (unsigned long long)gridDim.x * blockDim.x) {
+        const float x = __uint_as_float((unsigned)b);
+        float len = xsqrt(x);
+        if (len != 0) len = xrcp(len);
+        const float got = normalize_factor(x);
+        if (__float_as_uint(got) != __float_as_uint(len) && !(got != got && len != len)) {
+            if (!bad) atomicMin(first_bad, (unsigned)b);
+            ++bad;
+        }
+    }
+    if (bad) atomicAdd(mismatches, bad);
+}
+cudaError_t check_normalize_factor(unsigned long long* mismatches, unsigned* first_bad, int* launches) {
+    unsigned long long* d = nullptr;
+    cudaError_t e = cudaMalloc(&d, 16);
+    if (e != cudaSuccess) return e;
+    const unsigned long long init[2] = {0ull, 0xFFFFFFFFull};
+    e = cudaMemcpy(d, init, 16, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        check_normalize_factor_kernel<<<sm_count() * 8, 256>>>(d, reinterpret_cast<unsigned*>(d + 1));
+        if (launches) *launches += 1;
+        e = cudaGetLastError();
+    }
+    unsigned long long out[2] = {0, 0};
+    if (e == cudaSuccess) e = cudaMemcpy(out, d, 16, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    *mismatches = out[0];
+    *first_bad = (unsigned)out[1];
+    return e;
 }
 
 cudaError_t measure_fp32_peak(double* tflops, int* launches) {
