@@ -111,6 +111,8 @@ struct BokehView {
 // s_rows[2h + actual row] (staged by the caller, stage_row_finals): the same values from smaller / nearer places.
 template <bool kCompact = false>
 __device__ __forceinline__ void bokeh_sample(const BokehView& b, float u_row, float u_col, float* dx, float* dy) {
+    // (a straight-line form of the row search for brackets of at most two entries, like the column search below, is no
+    // faster: the row tables are in shared memory, there is no chain of long loads to shorten; profiles/r02_ab.txt call 26)
     int r = upper_bound_guided(b.h, b.row_shift, u_row, [&](int i) { return s_rows[i]; }, [&](int k) { return (int)__ldg(b.row_guide + k); });
     if (r >= b.h) r = b.h - 1;
     const int row = __float_as_int(s_rows[b.h + r]);
