@@ -471,17 +471,35 @@ def main():
             cam.create_rays_host(hs, seed=wl.seed, first_index=first, out=hr)
         torch.cuda.synchronize()
         dt = reduce_max((time.perf_counter() - t0) / reps)
-        e2e = {"value": world * m / dt / 1e6, "unit": UNIT, "h2d_bytes_per_step": 16 * m,
-               "d2h_bytes_per_step": 32 * m, "samples_per_step": m,
-               "api": "zoicb_generate_host (pinned host buffers, 3-slot copy/compute pipeline)"}
-        del hs, hr
+        records = {"value": world * m / dt / 1e6, "d2h_bytes_per_step": 32 * m, "seconds_per_step": dt,
+                   "api": "zoicb_generate_host (32-byte records)"}
+        del hr
+        # the same rays as planes: 25 bytes per ray on the link instead of 32 (include/zoicb.h: zoicb_ray_planes; lossless,
+        # tests/test_gpu_parity.py::test_planar_host_output_is_lossless).  The download bounds the end-to-end rate, so this
+        # is the call a host that wants the rays quickly makes: the headline e2e figure.
+        hp = torch.empty((6, m), dtype=torch.float32).pin_memory()
+        hf = torch.empty((m,), dtype=torch.uint8).pin_memory()
+        cam.create_rays_host_planar(hs, seed=wl.seed, first_index=first, planes=hp, flags=hf)   # warm-up
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            cam.create_rays_host_planar(hs, seed=wl.seed, first_index=first, planes=hp, flags=hf)
+        torch.cuda.synchronize()
+        dtp = reduce_max((time.perf_counter() - t0) / reps)
+        e2e = {"value": world * m / dtp / 1e6, "unit": UNIT, "h2d_bytes_per_step": 16 * m,
+               "d2h_bytes_per_step": 25 * m, "samples_per_step": m,
+               "api": "zoicb_generate_host_planar (pinned host buffers, 3-slot copy/compute pipeline; six float planes + one "
+                      "byte of tries / zero-weight flag per ray)",
+               "records_32B": records}
+        del hs, hp, hf
         try:
             y = pcie_yardstick(torch, dev, barrier, reduce_max)
-            per_rank_d2h = 32.0 * m / dt / 1e9
+            per_rank_d2h = 25.0 * m / dtp / 1e9
             e2e["pcie"] = y
             e2e["d2h_gbs_per_rank"] = per_rank_d2h
-            # the download (32 B/ray) is the binding direction; the upload (16 B/ray) shares the link at half its rate
+            # the download (25 B/ray; 32 with records) is the binding direction; the upload (16 B/ray) shares the link
             e2e["pcie_frac"] = per_rank_d2h / y["d2h_alone"]
+            records["pcie_frac"] = 32.0 * m / dt / 1e9 / y["d2h_alone"]
         except Exception as exc:   # a yardstick, not the measurement
             e2e["pcie"] = {"error": repr(exc)}
 

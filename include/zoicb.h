@@ -9,6 +9,7 @@
  *   zoicb_create        node_initialize + node_update            src/zoic.cpp:1565-1572, 1575-1720
  *   zoicb_generate      camera_create_ray, one call per BATCH    src/zoic.cpp:1752-1990
  *   zoicb_generate_host the same, host buffers in / out          src/zoic.cpp:1752-1990
+ *   zoicb_generate_host_planar   the same, 25-byte planar output  src/zoic.cpp:1752-1990
  *   zoicb_get_stats     the counters printed by node_finish      src/zoic.cpp:1729-1732
  *   zoicb_destroy       node_finish                              src/zoic.cpp:1723-1749
  *   zoicb_transform_rays  (the renderer's camera-to-world step after camera_create_ray; nothing in zoic)
@@ -163,6 +164,21 @@ ZOICB_API zoicb_status zoicb_generate(zoicb_ctx* ctx, const void* d_samples, uin
  * pinned staging chunks.  Synchronous. */
 ZOICB_API zoicb_status zoicb_generate_host(zoicb_ctx* ctx, const float* h_samples, uint64_t n, uint64_t first_index,
                                            uint64_t rng_seed, zoicb_ray* h_rays);
+
+/* zoicb_generate_host with PLANAR output: the same rays in 25 bytes instead of 32.  The host link carries every result,
+ * and at 32 bytes per ray the download is what bounds the end-to-end rate -- but two of the
+ * record's eight floats carry almost nothing: weight is 0 or the camera's exposure scale, tries is an integer <= 27.
+ *   origin[k][i], dir[k][i] : component k of ray i's origin / dir, bit for bit (n floats per plane)
+ *   flags[i]                : bits 0-6 = tries, bit 7 set <=> weight == 0                (n bytes)
+ * *live_weight (optional) receives the weight of the rays whose bit 7 is clear.  Planes may be pageable or pinned
+ * (pinned: copied directly); lossless: tests/test_gpu_parity.py rebuilds the 32-byte records from the planes. */
+typedef struct zoicb_ray_planes {
+    float* origin[3];
+    float* dir[3];
+    uint8_t* flags;
+} zoicb_ray_planes;
+ZOICB_API zoicb_status zoicb_generate_host_planar(zoicb_ctx* ctx, const float* h_samples, uint64_t n, uint64_t first_index,
+                                                  uint64_t rng_seed, const zoicb_ray_planes* out, float* live_weight);
 
 /* camera_create_ray for ONE sample (the shape of Arnold's per-sample callback): sample = (sx, sy, lensx,
  * lensy), one zoicb_ray in host memory.  Uses per-thread pinned staging and a per-thread

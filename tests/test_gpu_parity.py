@@ -147,6 +147,34 @@ def test_host_buffer_entry_point(port):
     ref.close()
 
 
+def test_planar_host_output_is_lossless():
+    """zoicb_generate_host_planar carries 25 bytes per ray over the host link instead of 32: the 32-byte records rebuilt
+    from the planes equal zoicb_generate_host's bit for bit -- raytraced and thin lens (vignetted rays: weight 0, many
+    tries), an exposure scale other than 1, pageable and pinned memory, more than one pipeline chunk."""
+    from zoic_b200 import ZoicCamera, unpack_planes
+    from zoic_b200.synth import hex_bokeh_image
+    from zoic_b200.workloads import lens_path
+    cams = [(None, dict(lensModel=1, lensDataPath=lens_path("double_gauss_f2.0.dat"), focalLength=5.0, fStop=2.0, exposureControl=0.7)),
+            (None, dict(lensModel=0, focalLength=2.0, fStop=1.4, opticalVignettingDistance=4.0, opticalVignettingRadius=0.6,
+                        exposureControl=-0.5)),
+            (hex_bokeh_image(33), dict(lensModel=0, focalLength=3.5, fStop=2.8, useImage=1, opticalVignettingDistance=2.0))]
+    for image, kw in cams:
+        cam = ZoicCamera(image=image, **kw)
+        n = (1 << 21) * 2 + 12_345          # three chunks of the host pipeline, the last one ragged
+        s = random_samples(n, seed=17)
+        want = cam.create_rays_host(s, seed=9, first_index=3)
+        planes, flags, w = cam.create_rays_host_planar(s, seed=9, first_index=3)            # pageable
+        got = unpack_planes(planes, flags, w)
+        assert bits_equal(got, want)
+        assert (flags & 0x80).any() or kw["lensModel"] == 1 or image is not None   # the harsh thin lens has zero-weight rays
+        sp = torch.from_numpy(s).pin_memory()
+        pp = torch.empty((6, n), dtype=torch.float32).pin_memory()
+        fp = torch.empty((n,), dtype=torch.uint8).pin_memory()
+        _, _, w2 = cam.create_rays_host_planar(sp, seed=9, first_index=3, planes=pp, flags=fp)   # pinned: direct DMA
+        assert w2 == w and bits_equal(unpack_planes(pp.numpy(), fp.numpy(), w2), want)
+        cam.close()
+
+
 def test_two_host_threads_share_a_camera_and_a_stream(port):
     """generate calls on one context from several host threads.  Two threads drive the SAME camera on the
     SAME (default) stream, guarded mode (counter reset + pool kernel + re-run kernel per call): every call's records must

@@ -5,4 +5,4 @@ adapter), the ctypes binding (capi), the host-side mirror of the camera node (ca
 workloads (synth).
 """
 from .camera import (ZoicCamera, Gather, build_bokeh_tables, debug_lut_boxes, host_setup, make_params, nccl_unique_id,  # noqa: F401
-                     split_rays, THINLENS, RAYTRACED, MODE_EXACT, MODE_GUARDED)
+                     split_rays, unpack_planes, THINLENS, RAYTRACED, MODE_EXACT, MODE_GUARDED)

@@ -78,6 +78,10 @@ GATHER_BLOB_BYTES, NCCL_ID_BYTES = 192, 128
 
 # every symbol include/zoicb.h declares: name -> (restype, argtypes)
 _P = C.c_void_p
+
+
+class RayPlanes(C.Structure):   # include/zoicb.h: zoicb_ray_planes
+    _fields_ = [("origin", C.c_void_p * 3), ("dir", C.c_void_p * 3), ("flags", C.c_void_p)]
 SYMBOLS = {
     "zoicb_default_params": (None, [C.POINTER(Params)]),
     "zoicb_create": (C.c_int, [C.POINTER(Params), _P, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_P)]),
@@ -87,6 +91,7 @@ SYMBOLS = {
     "zoicb_set_guard_scale": (C.c_int, [_P, C.c_float]),
     "zoicb_generate": (C.c_int, [_P, _P, C.c_uint64, C.c_uint64, C.c_uint64, _P, _P]),
     "zoicb_generate_host": (C.c_int, [_P, _P, C.c_uint64, C.c_uint64, C.c_uint64, _P]),
+    "zoicb_generate_host_planar": (C.c_int, [_P, _P, C.c_uint64, C.c_uint64, C.c_uint64, C.POINTER(RayPlanes), C.POINTER(C.c_float)]),
     "zoicb_generate_one": (C.c_int, [_P, _P, C.c_uint64, C.c_uint64, _P]),
     "zoicb_write_draw_file": (C.c_int, [_P, C.c_char_p, _P, C.c_uint32, _P, C.c_uint64, C.c_uint64]),
     "zoicb_transform_rays": (C.c_int, [_P, _P, C.c_uint64, _P, _P, _P]),

@@ -176,9 +176,10 @@ void free_ctx(zoicb_ctx* c) {
     cudaFree(c->d_stats);
     for (int s = 0; s < zoicb_ctx::kSlots; ++s) {
         if (c->streams[s]) cudaStreamDestroy(c->streams[s]);
-        cudaFree(c->d_in[s]); cudaFree(c->d_r[s]);
+        cudaFree(c->d_in[s]); cudaFree(c->d_r[s]); cudaFree(c->d_p[s]);
         if (c->h_in[s]) cudaFreeHost(c->h_in[s]);
         if (c->h_r[s]) cudaFreeHost(c->h_r[s]);
+        if (c->h_p[s]) cudaFreeHost(c->h_p[s]);
     }
     delete c;
 }
@@ -329,11 +330,14 @@ zoicb_status zoicb_generate(zoicb_ctx* ctx, const void* d_samples, uint64_t n, u
     return ZOICB_OK;
 }
 
-zoicb_status zoicb_generate_host(zoicb_ctx* ctx, const float* h_samples, uint64_t n, uint64_t first_index,
-                                 uint64_t rng_seed, zoicb_ray* h_rays) {
-    if (!ctx) return api_fail(ZOICB_ERR_INVALID_ARGUMENT, "zoicb_generate_host: null context");
-    if (n == 0) return ZOICB_OK;
-    if (!h_samples || !h_rays) return api_fail(ZOICB_ERR_INVALID_ARGUMENT, "zoicb_generate_host: null buffer");
+}  // extern "C"
+
+namespace {
+
+// zoicb_generate_host / zoicb_generate_host_planar: host samples in, host rays out, through a 3-slot pipeline of
+// upload / kernels / (pack) / download.  Exactly one of h_rays (32-byte records) and planes (25 bytes per ray) is set.
+zoicb_status generate_host_impl(zoicb_ctx* ctx, const float* h_samples, uint64_t n, uint64_t first_index, uint64_t rng_seed,
+                                zoicb_ray* h_rays, const zoicb_ray_planes* planes) {
     std::lock_guard<std::mutex> lock(ctx->host_mu);
     ZGUARD(ctx->device);
     constexpr int K = zoicb_ctx::kSlots;
@@ -349,23 +353,40 @@ zoicb_status zoicb_generate_host(zoicb_ctx* ctx, const float* h_samples, uint64_
             ZCUDA(cudaMalloc(&ctx->d_r[s], ctx->chunk * sizeof(RayRecord)), "cudaMalloc(staging)");
         }
     }
-    const bool direct = is_pinned_host(h_samples) && is_pinned_host(h_rays);
-    if (!direct && !ctx->h_in[0]) {
+    const uint64_t C = ctx->chunk;
+    // planar: device chunk = six float planes of C entries, then C bytes
+    if (planes && !ctx->d_p[0])
+        for (int s = 0; s < K; ++s) ZCUDA(cudaMalloc(&ctx->d_p[s], C * 25), "cudaMalloc(staging)");
+    void* const plane_ptr[7] = {planes ? planes->origin[0] : nullptr, planes ? planes->origin[1] : nullptr,
+                                planes ? planes->origin[2] : nullptr, planes ? planes->dir[0] : nullptr,
+                                planes ? planes->dir[1] : nullptr, planes ? planes->dir[2] : nullptr,
+                                planes ? (void*)planes->flags : nullptr};
+    bool direct = is_pinned_host(h_samples);
+    if (planes) { for (void* q : plane_ptr) direct = direct && is_pinned_host(q); }
+    else direct = direct && is_pinned_host(h_rays);
+    if (!direct) {
         for (int s = 0; s < K; ++s) {
-            ZCUDA(cudaMallocHost(&ctx->h_in[s], ctx->chunk * sizeof(float4)), "cudaMallocHost");
-            ZCUDA(cudaMallocHost(&ctx->h_r[s], ctx->chunk * sizeof(RayRecord)), "cudaMallocHost");
+            if (!ctx->h_in[s]) ZCUDA(cudaMallocHost(&ctx->h_in[s], C * sizeof(float4)), "cudaMallocHost");
+            if (!planes && !ctx->h_r[s]) ZCUDA(cudaMallocHost(&ctx->h_r[s], C * sizeof(RayRecord)), "cudaMallocHost");
+            if (planes && !ctx->h_p[s]) ZCUDA(cudaMallocHost(&ctx->h_p[s], C * 25), "cudaMallocHost");
         }
     }
-    const uint64_t nchunks = (n + ctx->chunk - 1) / ctx->chunk;
+    const uint64_t nchunks = (n + C - 1) / C;
     int launches = 0;
+    auto plane_bytes = [](int j) -> uint64_t { return j < 6 ? 4u : 1u; };
     // pageable callers: the copy-out of chunk k-K is drained just before slot reuse
     auto drain = [&](uint64_t k) -> cudaError_t {
         const int s = (int)(k % K);
         cudaError_t e = cudaStreamSynchronize(ctx->streams[s]);
         if (e != cudaSuccess) return e;
         if (!direct) {
-            const uint64_t b = k * ctx->chunk, m = (n - b < ctx->chunk) ? n - b : ctx->chunk;
-            std::memcpy(h_rays + b, ctx->h_r[s], m * sizeof(RayRecord));
+            const uint64_t b = k * C, m = (n - b < C) ? n - b : C;
+            if (planes) {
+                for (int j = 0; j < 7; ++j)
+                    std::memcpy(static_cast<char*>(plane_ptr[j]) + b * plane_bytes(j), ctx->h_p[s] + (uint64_t)j * 4u * C, m * plane_bytes(j));
+            } else {
+                std::memcpy(h_rays + b, ctx->h_r[s], m * sizeof(RayRecord));
+            }
         }
         return cudaSuccess;
     };
@@ -378,7 +399,7 @@ zoicb_status zoicb_generate_host(zoicb_ctx* ctx, const float* h_samples, uint64_
             const int s = (int)(k % K);
             what = "pipeline drain";
             if (k >= (uint64_t)K && (e = drain(k - K)) != cudaSuccess) return e;
-            const uint64_t b = k * ctx->chunk, m = (n - b < ctx->chunk) ? n - b : ctx->chunk;
+            const uint64_t b = k * C, m = (n - b < C) ? n - b : C;
             const float* src = h_samples + 4 * b;
             if (!direct) { std::memcpy(ctx->h_in[s], src, m * sizeof(float4)); src = (const float*)ctx->h_in[s]; }
             what = "H2D";
@@ -392,9 +413,17 @@ zoicb_status zoicb_generate_host(zoicb_ctx* ctx, const float* h_samples, uint64_
                 if ((e = launch_generate(ctx->host.state, ctx->mode, ctx->d_in[s], m, first_index + b, rng_seed, ctx->d_r[s],
                                          ctx->d_stats, ctx->streams[s], ws, &launches)) != cudaSuccess) return e;
             }
-            void* dst = direct ? (void*)(h_rays + b) : (void*)ctx->h_r[s];
             what = "D2H";
-            if ((e = cudaMemcpyAsync(dst, ctx->d_r[s], m * sizeof(RayRecord), cudaMemcpyDeviceToHost, ctx->streams[s])) != cudaSuccess) return e;
+            if (planes) {
+                if ((e = launch_pack_planar(ctx->d_r[s], m, C, ctx->d_p[s], ctx->streams[s], &launches)) != cudaSuccess) return e;
+                for (int j = 0; j < 7; ++j) {   // plane j of the chunk starts at byte 4 j C (the byte plane last)
+                    void* dst = direct ? (void*)(static_cast<char*>(plane_ptr[j]) + b * plane_bytes(j)) : (void*)(ctx->h_p[s] + (uint64_t)j * 4u * C);
+                    if ((e = cudaMemcpyAsync(dst, ctx->d_p[s] + (uint64_t)j * 4u * C, m * plane_bytes(j), cudaMemcpyDeviceToHost, ctx->streams[s])) != cudaSuccess) return e;
+                }
+            } else {
+                void* dst = direct ? (void*)(h_rays + b) : (void*)ctx->h_r[s];
+                if ((e = cudaMemcpyAsync(dst, ctx->d_r[s], m * sizeof(RayRecord), cudaMemcpyDeviceToHost, ctx->streams[s])) != cudaSuccess) return e;
+            }
         }
         what = "pipeline drain";
         for (uint64_t k = (nchunks > (uint64_t)K ? nchunks - K : 0); k < nchunks; ++k)
@@ -409,6 +438,30 @@ zoicb_status zoicb_generate_host(zoicb_ctx* ctx, const float* h_samples, uint64_
         return api_cuda_fail(e, what);
     }
     return ZOICB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+zoicb_status zoicb_generate_host(zoicb_ctx* ctx, const float* h_samples, uint64_t n, uint64_t first_index,
+                                 uint64_t rng_seed, zoicb_ray* h_rays) {
+    if (!ctx) return api_fail(ZOICB_ERR_INVALID_ARGUMENT, "zoicb_generate_host: null context");
+    if (n == 0) return ZOICB_OK;
+    if (!h_samples || !h_rays) return api_fail(ZOICB_ERR_INVALID_ARGUMENT, "zoicb_generate_host: null buffer");
+    return generate_host_impl(ctx, h_samples, n, first_index, rng_seed, h_rays, nullptr);
+}
+
+zoicb_status zoicb_generate_host_planar(zoicb_ctx* ctx, const float* h_samples, uint64_t n, uint64_t first_index,
+                                        uint64_t rng_seed, const zoicb_ray_planes* out, float* live_weight) {
+    if (!ctx) return api_fail(ZOICB_ERR_INVALID_ARGUMENT, "zoicb_generate_host_planar: null context");
+    if (live_weight) *live_weight = ctx->host.state.weight_scale;   // weight = {1, 0} * the exposure scale, in every kernel
+    if (n == 0) return ZOICB_OK;
+    if (!h_samples || !out) return api_fail(ZOICB_ERR_INVALID_ARGUMENT, "zoicb_generate_host_planar: null buffer");
+    for (int k = 0; k < 3; ++k)
+        if (!out->origin[k] || !out->dir[k]) return api_fail(ZOICB_ERR_INVALID_ARGUMENT, "zoicb_generate_host_planar: null plane");
+    if (!out->flags) return api_fail(ZOICB_ERR_INVALID_ARGUMENT, "zoicb_generate_host_planar: null plane");
+    return generate_host_impl(ctx, h_samples, n, first_index, rng_seed, nullptr, out);
 }
 
 namespace {

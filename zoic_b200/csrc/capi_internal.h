@@ -40,6 +40,8 @@ struct zoicb_ctx {
     zoicb::RayRecord* d_r[kSlots] = {nullptr, nullptr, nullptr};
     float4* h_in[kSlots] = {nullptr, nullptr, nullptr};   // pinned staging, only for pageable callers
     zoicb::RayRecord* h_r[kSlots] = {nullptr, nullptr, nullptr};
+    uint8_t* d_p[kSlots] = {nullptr, nullptr, nullptr};   // planar form of a chunk (zoicb_generate_host_planar): 25 bytes per ray
+    uint8_t* h_p[kSlots] = {nullptr, nullptr, nullptr};   // pinned staging of the same, only for pageable callers
     std::mutex host_mu;
     // optional: events recorded around the device-side bokeh table build (zoicb_build_bokeh_tables)
     cudaEvent_t bokeh_ev0 = nullptr, bokeh_ev1 = nullptr;

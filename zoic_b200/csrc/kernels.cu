@@ -471,6 +471,22 @@ transform_rays_kernel(const __grid_constant__ Xform X, const RayRecord* __restri
 }
 
 // ------------------------------------------------------------------------------------------------
+// records -> planes for the host link (include/zoicb.h: zoicb_ray_planes): the 32-byte record carries two floats that
+// take two values (weight) and twenty-eight (tries); on the wire they are one byte
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+pack_planar_kernel(const RayRecord* __restrict__ rays, uint64_t n, uint64_t stride, float* __restrict__ planes, uint8_t* __restrict__ flags) {
+    const uint64_t step = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) {
+        float4 o, d;
+        load_ray(rays, i, &o, &d);
+        planes[i] = o.x; planes[stride + i] = o.y; planes[2 * stride + i] = o.z;
+        planes[3 * stride + i] = d.x; planes[4 * stride + i] = d.y; planes[5 * stride + i] = d.z;
+        flags[i] = (uint8_t)(((unsigned)(int)d.w & 0x7Fu) | (o.w == 0.0f ? 0x80u : 0u));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // fp32 peak probe: 8 independent FFMA chains per thread
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) ffma_peak_kernel(float* out, int iters, float a, float b) {
@@ -648,6 +664,13 @@ cudaError_t launch_lut_bbox(const uint32_t* d_draws, const uint8_t* d_accept, in
                             float4* d_boxes, cudaStream_t st, int* launches) {
     if (n_film <= 0) return cudaSuccess;
     lut_bbox_kernel<<<n_film, 32, 0, st>>>(d_draws, d_accept, per_film, ap, d_boxes);
+    if (launches) *launches += 1;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_pack_planar(const RayRecord* rays, uint64_t n, uint64_t stride, uint8_t* planes, cudaStream_t st, int* launches) {
+    if (n == 0) return cudaSuccess;
+    pack_planar_kernel<<<grid_for(n, 256, 8), 256, 0, st>>>(rays, n, stride, reinterpret_cast<float*>(planes), planes + 24 * stride);
     if (launches) *launches += 1;
     return cudaGetLastError();
 }

@@ -59,6 +59,8 @@ cudaError_t launch_bokeh_build(const float* d_rgb, int w, int h, int nch, float*
 cudaError_t launch_differentials(const CameraState& cam, const float4* samples, uint64_t n, uint64_t first_index, uint64_t seed,
                                  float dsx, float dsy, const RayRecord* rays, float4* out, cudaStream_t st, int* launches);
 cudaError_t launch_transform_diffs(const float* m3x4, const float4* in, uint64_t n, float4* out, cudaStream_t st, int* launches);
+// records -> planes (zoicb_generate_host_planar): six float planes of `stride` entries each, then `stride` bytes of flags
+cudaError_t launch_pack_planar(const RayRecord* rays, uint64_t n, uint64_t stride, uint8_t* planes, cudaStream_t st, int* launches);
 cudaError_t check_normalize_factor(unsigned long long* mismatches, unsigned* first_bad, int* launches);
 cudaError_t measure_fp32_peak(double* tflops, int* launches);
 
