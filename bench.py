@@ -424,14 +424,16 @@ def main():
         # runs another kernel (exact_kernel), for which there is no capture
         key = "kolb" if model == 1 else ("thin" if wl.params.get("opticalVignettingDistance", 0.0) > 0.0 else None)
         if key in cap:
-            src = os.path.join(ROOT, "zoic_b200", "csrc", cap[key].get("source", "kolb_pool2.cu"))
+            # the kernel's translation unit and the headers its code comes from (comma-separated in traffic.json)
+            src = cap[key].get("source", "kolb_pool2.cu")
             import hashlib
-            digest = hashlib.sha1(open(src, "rb").read()).hexdigest()[:12]
+            digest = hashlib.sha1(b"".join(open(os.path.join(ROOT, "zoic_b200", "csrc", f), "rb").read()
+                                           for f in src.split(","))).hexdigest()[:12]
             if cap[key].get("source_sha1", digest) == digest:
                 traffic = cap[key]["dram_bytes_per_ray"] * n
                 traffic_note = "ncu capture %s at commit %s" % (cap[key].get("capture"), cap[key].get("commit"))
             else:
-                traffic_note = "profiles/traffic.json was captured for another version of %s: not used" % os.path.basename(src)
+                traffic_note = "profiles/traffic.json was captured for another version of %s: not used" % src
     except Exception:
         pass
     per_launch = {"rays_per_launch": min(n, tile) if not resident else n,

@@ -57,7 +57,8 @@ for cap, out in ((tag + "_ncu_pool2.ncu-rep", name + "_ncu_main_raw.csv"), (tag 
 # 3. traffic.json: DRAM bytes per ray of the dominant kernels, tied to the source they were captured from (bench.py refuses a
 # capture whose kernel source has changed since)
 import hashlib
-def sha(path): return hashlib.sha1(open(path, "rb").read()).hexdigest()[:12]
+HEADERS = "kernel_common.cuh,lens_math.cuh,camera_state.h"   # where most of both kernels' code lives
+def sha(files): return hashlib.sha1(b"".join(open(os.path.join("zoic_b200/csrc", f), "rb").read() for f in files.split(","))).hexdigest()[:12]
 commit = subprocess.run(["git", "rev-parse", "--short", "HEAD"], capture_output=True, text=True).stdout.strip()
 traffic = {}
 def per_ray(csv_path, kernel_sub, rays):
@@ -72,14 +73,14 @@ hp = os.path.join(G, tag + "_launches_headline.csv")
 if os.path.exists(hp):
     v = per_ray(hp, "kolb_pool2_kernel", 2123366400)
     if v:
-        traffic["kolb"] = {"dram_bytes_per_ray": round(v[0], 3), "source": "kolb_pool2.cu", "source_sha1": sha("zoic_b200/csrc/kolb_pool2.cu"),
+        traffic["kolb"] = {"dram_bytes_per_ray": round(v[0], 3), "source": "kolb_pool2.cu," + HEADERS, "source_sha1": sha("kolb_pool2.cu," + HEADERS),
                            "commit": commit, "capture": "profiles/%s_launches_headline.csv" % name,
                            "what": "dram__bytes_read.sum + dram__bytes_write.sum of the last kolb_pool2_kernel launch (2,123,366,400 rays); algorithmic 48 B/ray"}
 cp = os.path.join(G, tag + "_launches_config3.csv")
 if os.path.exists(cp):
-    v = per_ray(cp, "thin_persistent_kernel", 2123366400)
+    v = per_ray(cp, "thin_persistent_kernel", 2123366400)   # whichever instantiation ran
     if v:
-        traffic["thin"] = {"dram_bytes_per_ray": round(v[0], 3), "source": "kernels.cu", "source_sha1": sha("zoic_b200/csrc/kernels.cu"),
+        traffic["thin"] = {"dram_bytes_per_ray": round(v[0], 3), "source": "kernels.cu," + HEADERS, "source_sha1": sha("kernels.cu," + HEADERS),
                                  "commit": commit, "capture": "profiles/%s_launches_config3.csv" % name,
                                  "what": "dram__bytes_read.sum + dram__bytes_write.sum of the last thin_persistent_kernel<1> launch (2,123,366,400 rays); algorithmic 48 B/ray"}
     rows = [r for r in csv.reader(open(cp, errors="replace")) if len(r) > 14 and r[0].isdigit()]
