@@ -150,9 +150,6 @@ kolb_exact_persistent_kernel(const __grid_constant__ CameraState cam, const floa
 #define ZOICB_THIN_CTAS 6   // resident CTAs of 8 warps per SM: 48 warps at <= 40 registers (4 -> 5 -> 6: 14.7 -> 16.3 -> 17.2 Grays/s on
                            // config 3, profiles/r01b_ab.txt; 8 spills)
 #endif
-#ifndef ZOICB_THIN_RING_DEFAULT
-#define ZOICB_THIN_RING_DEFAULT 0
-#endif
 #ifndef ZOICB_THIN_MERGED_NORM
 #define ZOICB_THIN_MERGED_NORM 1
 #endif
@@ -242,194 +239,6 @@ thin_persistent_kernel(const __grid_constant__ CameraState cam, const float4* __
             }
         }
     }
-    flush_stats(ls, stats);
-}
-
-// The same kernel with a PRODUCER WARP.  What a sample costs before its first attempt (pinhole direction, focus point)
-// and at its first retry (seeding its stream) is executed above by the few lanes that need it in an iteration -- 10.6 and
-// 5.8 of 32 on config 3, a quarter of the kernel's warp instructions.  Here warp 0 of every CTA does that work for all
-// the others, 32 samples at a time with every lane busy, and hands the results over through a small ring in shared memory
-// (64 entries of 48 bytes: focus point, first lens sample, seeded stream, sample index, sequence word); warps 1-7 only run
-// attempts.  Entry e lives in slot e % 64; its sequence word is e + 1 while the entry is full and 0 when the slot is free:
-// the producer waits for 0 before it writes, a consumer that claimed e (one shared-memory atomicAdd per warp and
-// iteration) waits for e + 1, reads, and writes 0.  The arithmetic per sample is the same, so the records are.
-constexpr unsigned kRing = 64;
-__device__ __forceinline__ unsigned lds_volatile(const unsigned* p) {
-    unsigned v;
-    asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"((unsigned)__cvta_generic_to_shared(p)) : "memory");
-    return v;
-}
-__device__ __forceinline__ void sts_volatile(unsigned* p, unsigned v) {
-    asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(p)), "r"(v) : "memory");
-}
-template <bool kImage, bool kCompact>
-__global__ void __launch_bounds__(256, ZOICB_THIN_CTAS)
-thin_ring_kernel(const __grid_constant__ CameraState cam, const float4* __restrict__ samples, uint64_t n,
-                 uint64_t first_index, uint64_t seed, RayRecord* __restrict__ rays,
-                 DeviceStats* stats, unsigned long long* chunk_counter) {
-    __shared__ uint4 s_ring[kRing * 3];
-    __shared__ unsigned s_sync[4];   // [0] entries claimed by consumers, [1] producer done, [2] entries produced in all, [3] produced so far
-    if (threadIdx.x < 4) s_sync[threadIdx.x] = 0u;
-    for (unsigned i = threadIdx.x; i < kRing; i += blockDim.x) s_ring[i * 3 + 2] = make_uint4(0u, 0u, 0u, 0u);
-    BokehView bk;
-    if (kImage) bk = stage_bokeh(cam);
-    else __syncthreads();
-    if (kImage && kCompact) stage_row_finals(cam);
-    const ThinState& T = cam.thin;
-    const unsigned lane = threadIdx.x & 31;
-    LocalStats ls = {0, 0, 0, 0, 0, 0, 0};
-    constexpr unsigned kSpinLimit = 1u << 24;   // polls; a ring that does not move for this long is a bug: trap, do not hang
-
-    if ((threadIdx.x >> 5) == 0) {
-        // ---------------------------------------------------------------- producer
-        unsigned p = 0;   // entries produced so far
-        for (;;) {
-            unsigned long long base = 0;
-            if (lane == 0) base = atomicAdd(chunk_counter, (unsigned long long)kChunk);
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (base >= n) break;
-            const uint64_t end = (base + kChunk < n) ? base + kChunk : n;
-            // two blocks of 32 per round: the two samples of a lane are independent chains (a root, a reciprocal, a
-            // division, two 64-bit mixes each), so one warp keeps up with the seven it feeds
-            for (uint64_t b = base; b < end; b += 64) {
-                const uint64_t j0 = b + lane, j1 = b + 32 + lane;
-                const bool v0 = j0 < end, v1 = j1 < end;
-                const unsigned n0 = (unsigned)((end - b < 32) ? end - b : 32), n1 = (unsigned)((end - b < 64) ? end - b : 64) - n0;
-                const unsigned e0 = p + lane, e1 = p + n0 + lane;
-                const unsigned slot0 = e0 & (kRing - 1), slot1 = e1 & (kRing - 1);
-                float4 sa = make_float4(0.0f, 0.0f, 0.0f, 0.0f), sb = sa;
-                if (v0) sa = __ldcs(samples + j0);
-                if (v1) sb = __ldcs(samples + j1);
-                if (j0 + 64 < n) asm volatile("prefetch.global.L2 [%0];" ::"l"(samples + j0 + 64));
-                if (j1 + 64 < n) asm volatile("prefetch.global.L2 [%0];" ::"l"(samples + j1 + 64));
-                const Vec3 da = ZOICB_THIN_NORMALIZE(vmake(xmul(sa.x, T.tan_fov), xmul(sa.y, T.tan_fov), 1.0f));
-                const Vec3 db = ZOICB_THIN_NORMALIZE(vmake(xmul(sb.x, T.tan_fov), xmul(sb.y, T.tan_fov), 1.0f));
-                const Vec3 fa = vscale(da, fabsf(xdiv(T.focal_distance, da.z)));
-                const Vec3 fb = vscale(db, fabsf(xdiv(T.focal_distance, db.z)));
-                const Xor128 ra = sample_stream(seed, first_index + j0);
-                const Xor128 rb = sample_stream(seed, first_index + j1);
-                unsigned spins = 0;
-                while (__any_sync(0xffffffffu, (v0 && lds_volatile(&s_ring[slot0 * 3 + 2].w) != 0u) ||
-                                               (v1 && lds_volatile(&s_ring[slot1 * 3 + 2].w) != 0u))) {
-                    __nanosleep(64);
-                    if (++spins > kSpinLimit) __trap();
-                }
-                if (v0) {
-                    s_ring[slot0 * 3] = make_uint4(__float_as_uint(fa.x), __float_as_uint(fa.y), __float_as_uint(fa.z), __float_as_uint(sa.z));
-                    s_ring[slot0 * 3 + 1] = make_uint4(__float_as_uint(sa.w), ra.x, ra.y, ra.z);
-                    s_ring[slot0 * 3 + 2].x = ra.w; s_ring[slot0 * 3 + 2].y = (unsigned)j0; s_ring[slot0 * 3 + 2].z = (unsigned)(j0 >> 32);
-                }
-                if (v1) {
-                    s_ring[slot1 * 3] = make_uint4(__float_as_uint(fb.x), __float_as_uint(fb.y), __float_as_uint(fb.z), __float_as_uint(sb.z));
-                    s_ring[slot1 * 3 + 1] = make_uint4(__float_as_uint(sb.w), rb.x, rb.y, rb.z);
-                    s_ring[slot1 * 3 + 2].x = rb.w; s_ring[slot1 * 3 + 2].y = (unsigned)j1; s_ring[slot1 * 3 + 2].z = (unsigned)(j1 >> 32);
-                }
-                __threadfence_block();
-                if (v0) sts_volatile(&s_ring[slot0 * 3 + 2].w, e0 + 1u);
-                if (v1) sts_volatile(&s_ring[slot1 * 3 + 2].w, e1 + 1u);
-                p += n0 + n1;
-                __syncwarp();
-                if (lane == 0) sts_volatile(&s_sync[3], p);   // what consumers may claim without waiting
-            }
-        }
-        if (lane == 0) {
-            sts_volatile(&s_sync[2], p);
-            __threadfence_block();
-            sts_volatile(&s_sync[1], 1u);
-        }
-    } else {
-        // ---------------------------------------------------------------- consumers
-        bool have = false, finished = false;   // finished: the ring has run dry for this lane
-        uint64_t idx = 0;
-        Vec3 focus = vmake(0.0f, 0.0f, 0.0f);
-        Xor128 rng = {0, 0, 0, 0};
-        int tries = 0;   // -1: adopted, first attempt (its lens sample is the camera sample's own) still to come
-        float ua = 0.0f, ub = 0.0f;
-        for (;;) {
-            const unsigned need = __ballot_sync(0xffffffffu, !have && !finished);
-            if (need) {
-                // claim what the ring HOLDS, not what the warp would like: lanes that get nothing sit this iteration out
-                // (like the end of a chunk in the kernel above) instead of making the lanes with live rays wait for the
-                // producer.  Only a warp without any live ray waits.  After the producer's last entry every claim is
-                // served at once: entries below the final count are there, the others retire their lanes.
-                unsigned t = 0, take = 0;
-                if (lane == 0) {
-                    const unsigned want = (unsigned)__popc(need);
-                    if (lds_volatile(&s_sync[1]) != 0u) take = want;
-                    else {
-                        const unsigned prod = lds_volatile(&s_sync[3]), cl = lds_volatile(&s_sync[0]);
-                        const unsigned avail = prod > cl ? prod - cl : 0u;
-                        take = want < avail ? want : avail;
-                    }
-                    if (take) t = atomicAdd(&s_sync[0], take);
-                }
-                take = __shfl_sync(0xffffffffu, take, 0);
-                t = __shfl_sync(0xffffffffu, t, 0);
-                if (take == 0u) {
-                    if (!__any_sync(0xffffffffu, have)) { __nanosleep(100); continue; }   // nothing to do yet
-                }
-                unsigned lt_mask;
-                asm volatile("mov.u32 %0, %%lanemask_lt;" : "=r"(lt_mask));
-                const unsigned rank = (unsigned)__popc(need & lt_mask);
-                const unsigned e = t + rank, slot = e & (kRing - 1);
-                bool waiting = !have && !finished && rank < take;
-                unsigned spins = 0;
-                for (;;) {
-                    if (waiting) {
-                        if (lds_volatile(&s_ring[slot * 3 + 2].w) == e + 1u) {
-                            // read and free the slot AT ONCE: a lane that held its entry until the warp's other lanes had
-                            // theirs would keep the producer (which may need this very slot for those lanes) waiting
-                            __threadfence_block();
-                            const uint4 q0 = s_ring[slot * 3], q1 = s_ring[slot * 3 + 1], q2 = s_ring[slot * 3 + 2];
-                            __threadfence_block();
-                            sts_volatile(&s_ring[slot * 3 + 2].w, 0u);
-                            focus = vmake(__uint_as_float(q0.x), __uint_as_float(q0.y), __uint_as_float(q0.z));
-                            ua = __uint_as_float(q0.w);
-                            ub = __uint_as_float(q1.x);
-                            rng.x = q1.y; rng.y = q1.z; rng.z = q1.w; rng.w = q2.x;
-                            idx = (uint64_t)q2.y | ((uint64_t)q2.z << 32);
-                            tries = -1;
-                            have = true;
-                            waiting = false;
-                        } else if (lds_volatile(&s_sync[1]) != 0u && e >= lds_volatile(&s_sync[2])) {
-                            waiting = false;
-                            finished = true;
-                        }
-                    }
-                    if (!__any_sync(0xffffffffu, waiting)) break;
-                    __nanosleep(32);   // leave the issue slots to the producer
-                    if (++spins > kSpinLimit) __trap();
-                }
-            }
-            if (!__any_sync(0xffffffffu, have)) {
-                if (__all_sync(0xffffffffu, finished)) break;
-                continue;
-            }
-            if (have) {
-                if (tries >= 0) draw_pair(rng, &ua, &ub);
-                ++tries;
-            }
-            float lx, ly;
-            lens_sample<kImage, kCompact>(bk, ua, ub, &lx, &ly);
-            const Vec3 origin = vmake(xmul(lx, T.aperture_radius), xmul(ly, T.aperture_radius), 0.0f);
-            const Vec3 dir = ZOICB_THIN_NORMALIZE(vsub(focus, origin));
-            const float qx = xsub(xmul(dir.x, T.ov_distance), origin.x);
-            const float qy = xsub(xmul(dir.y, T.ov_distance), origin.y);
-            const bool pass = xadd(xmul(qx, qx), xmul(qy, qy)) < T.ov_s_threshold;   // camera_state.h: ov_s_threshold
-            if (have) {
-                ls.attempts++;
-                if (pass || tries > kMaxTries) {
-                    float weight = 1.0f;
-                    if (tries > kMaxTries) { weight = 0.0f; ls.vignetted++; }
-                    else ls.success++;
-                    weight = xmul(weight, cam.weight_scale);
-                    store_ray(rays, idx, make_float4(origin.x, origin.y, origin.z, weight), make_float4(dir.x, dir.y, -dir.z, (float)tries));
-                    have = false;
-                }
-            }
-        }
-    }
-    ls.rays = ls.success + ls.vignetted;
     flush_stats(ls, stats);
 }
 
@@ -757,24 +566,6 @@ static cudaError_t launch_variant(const CameraState& cam, int mode, const float4
         // (call 21) for finished lanes to adopt -- save 6-12 % of the warp instructions, stay bit-exact and lose to the
         // registers / the L2 round trip they cost: profiles/r02_ab.txt)
         const unsigned grid = (unsigned)sm_count() * ZOICB_THIN_CTAS;
-        static const bool ring = [] { const char* v = getenv("ZOICB_THIN_RING"); return v ? atoi(v) != 0 : (ZOICB_THIN_RING_DEFAULT != 0); }();
-        if (ring) {
-            const size_t need_r = (size_t)ZOICB_THIN_CTAS * (smem_k + 2200 + kRing * 48);
-            int pct_r = carve >= 0 ? carve : (int)((need_r * 100 + 233471) / 233472);
-            if (pct_r > 100) pct_r = 100;
-            if constexpr (kImage) {
-                if (compact) {
-                    cudaFuncSetAttribute(thin_ring_kernel<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct_r);
-                    thin_ring_kernel<true, true><<<grid, threads, smem_k, st>>>(cam, samples, n, first_index, seed, rays, stats, ws.counters);
-                    if (launches) *launches += 1;
-                    return cudaGetLastError();
-                }
-                cudaFuncSetAttribute(thin_ring_kernel<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct_r);
-            }
-            thin_ring_kernel<kImage, false><<<grid, threads, smem_k, st>>>(cam, samples, n, first_index, seed, rays, stats, ws.counters);
-            if (launches) *launches += 1;
-            return cudaGetLastError();
-        }
         if constexpr (kImage) {
             if (compact) {
                 cudaFuncSetAttribute(thin_persistent_kernel<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
