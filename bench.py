@@ -459,7 +459,8 @@ def main():
     if not args.no_e2e:
         m = min(args.e2e_samples, n)
         hs = torch.empty((m, 4), dtype=torch.float32).pin_memory()
-        hr = torch.empty((m, 8), dtype=torch.float32).pin_memory()
+        hout = torch.empty((32 * m,), dtype=torch.uint8).pin_memory()   # one pinned result buffer for both host formats
+        hr = hout.view(torch.float32).view(m, 8)
         if resident:
             hs.copy_(samples[:m])
         else:
@@ -475,12 +476,11 @@ def main():
         dt = reduce_max((time.perf_counter() - t0) / reps)
         records = {"value": world * m / dt / 1e6, "d2h_bytes_per_step": 32 * m, "seconds_per_step": dt,
                    "api": "zoicb_generate_host (32-byte records)"}
-        del hr
         # the same rays as planes: 25 bytes per ray on the link instead of 32 (include/zoicb.h: zoicb_ray_planes; lossless,
         # tests/test_gpu_parity.py::test_planar_host_output_is_lossless).  The download bounds the end-to-end rate, so this
         # is the call a host that wants the rays quickly makes: the headline e2e figure.
-        hp = torch.empty((6, m), dtype=torch.float32).pin_memory()
-        hf = torch.empty((m,), dtype=torch.uint8).pin_memory()
+        hp = hout[:24 * m].view(torch.float32).view(6, m)
+        hf = hout[24 * m:25 * m]
         cam.create_rays_host_planar(hs, seed=wl.seed, first_index=first, planes=hp, flags=hf)   # warm-up
         barrier()
         t0 = time.perf_counter()
@@ -493,7 +493,7 @@ def main():
                "api": "zoicb_generate_host_planar (pinned host buffers, 3-slot copy/compute pipeline; six float planes + one "
                       "byte of tries / zero-weight flag per ray)",
                "records_32B": records}
-        del hs, hp, hf
+        del hs, hr, hp, hf, hout
         try:
             y = pcie_yardstick(torch, dev, barrier, reduce_max)
             per_rank_d2h = 25.0 * m / dtp / 1e9
