@@ -40,14 +40,16 @@ def test_struct_layouts_match_the_header():
     src = r'''
     #include <stdio.h>
     #include "zoicb.h"
-    int main(void){ printf("%zu %zu %zu %zu\n", sizeof(zoicb_params), sizeof(zoicb_stats), sizeof(zoicb_constants), sizeof(zoicb_ray)); return 0; }
+    int main(void){ printf("%zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(zoicb_params), sizeof(zoicb_stats), sizeof(zoicb_constants), sizeof(zoicb_ray),
+                            sizeof(zoicb_job), sizeof(zoicb_job_result), sizeof(zoicb_ray_planes), sizeof(zoicb_ray_diff)); return 0; }
     '''
     import tempfile
     with tempfile.TemporaryDirectory() as d:
         open(os.path.join(d, "t.c"), "w").write(src)
         subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), os.path.join(d, "t.c"), "-o", os.path.join(d, "t")], check=True)
         sizes = [int(x) for x in subprocess.run([os.path.join(d, "t")], capture_output=True, text=True, check=True).stdout.split()]
-    assert sizes == [C.sizeof(capi.Params), C.sizeof(capi.Stats), C.sizeof(capi.Constants), C.sizeof(capi.Ray)]
+    assert sizes == [C.sizeof(capi.Params), C.sizeof(capi.Stats), C.sizeof(capi.Constants), C.sizeof(capi.Ray),
+                     C.sizeof(capi.Job), C.sizeof(capi.JobResult), C.sizeof(capi.RayPlanes), 48]
     assert C.sizeof(capi.Ray) == 32
 
 
@@ -73,6 +75,26 @@ def test_no_gpu_fails_loudly():
         ZoicCamera(lensModel=0, focalLength=3.5, fStop=2.8)
     assert e.value.code == capi.ERR_CUDA
     assert "no CPU fallback" in str(e.value)
+
+
+def test_planar_host_format_unpacks_to_the_records():
+    """include/zoicb.h zoicb_ray_planes: six float planes + one byte (bits 0-6 tries, bit 7: weight is 0).  A numpy
+    statement of the device's packing (kernels.cu: pack_planar_kernel) against zoic_b200.unpack_planes, on records with every
+    tries value, both weights, NaN and negative-zero components."""
+    import numpy as np
+    from zoic_b200 import unpack_planes
+    rng = np.random.default_rng(3)
+    n, w = 4096, np.float32(1.49)
+    rec = rng.standard_normal((n, 8)).astype(np.float32)
+    rec[:, 7] = rng.integers(0, 28, n).astype(np.float32)
+    rec[:, 3] = np.where(rng.random(n) < 0.3, np.float32(0.0), w)
+    rec[5, 0] = np.float32("nan"); rec[6, 4] = np.float32(-0.0); rec[7, 5] = np.float32("inf")
+    planes = np.ascontiguousarray(rec[:, [0, 1, 2, 4, 5, 6]].T)
+    flags = (rec[:, 7].astype(np.int32) & 0x7F).astype(np.uint8) | np.where(rec[:, 3] == 0, 0x80, 0).astype(np.uint8)
+    back = unpack_planes(planes, flags, w)
+    assert back.view(np.uint32).tolist() == rec.view(np.uint32).tolist()
+    lib = capi.load()
+    assert lib.zoicb_generate_host_planar(None, None, 1, 0, 0, None, None) == capi.ERR_INVALID_ARGUMENT
 
 
 def test_null_arguments_are_rejected():
