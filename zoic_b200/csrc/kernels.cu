@@ -150,6 +150,10 @@ kolb_exact_persistent_kernel(const __grid_constant__ CameraState cam, const floa
 #define ZOICB_THIN_CTAS 6   // resident CTAs of 8 warps per SM: 48 warps at <= 40 registers (4 -> 5 -> 6: 14.7 -> 16.3 -> 17.2 Grays/s on
                            // config 3, profiles/r01b_ab.txt; 8 spills)
 #endif
+#ifndef ZOICB_THIN_CTAS_COMPACT
+#define ZOICB_THIN_CTAS_COMPACT 8   // the kernel with byte-wide tables fits 32 registers without a spill: 64 warps per SM
+                                   // (6 / 7 / 8 CTAs: 25.4 / 25.6 / 26.1 Grays/s at 32 spp, profiles/r02_ab.txt call 30)
+#endif
 #ifndef ZOICB_THIN_MERGED_NORM
 #define ZOICB_THIN_MERGED_NORM 1
 #endif
@@ -160,7 +164,7 @@ kolb_exact_persistent_kernel(const __grid_constant__ CameraState cam, const floa
 #endif
 // kCompact: byte-wide column tables and the rows' final CDF values in shared memory (camera_state.h: BokehCompact)
 template <bool kImage, bool kCompact>
-__global__ void __launch_bounds__(256, ZOICB_THIN_CTAS)
+__global__ void __launch_bounds__(256, kCompact ? ZOICB_THIN_CTAS_COMPACT : ZOICB_THIN_CTAS)
 thin_persistent_kernel(const __grid_constant__ CameraState cam, const float4* __restrict__ samples, uint64_t n,
                        uint64_t first_index, uint64_t seed, RayRecord* __restrict__ rays,
                        DeviceStats* stats, int stage_rows, unsigned long long* chunk_counter) {
@@ -558,14 +562,15 @@ static cudaError_t launch_variant(const CameraState& cam, int mode, const float4
         static const bool allow_compact = [] { const char* v = getenv("ZOICB_THIN_COMPACT"); return !v || atoi(v) != 0; }();
         const bool compact = kImage && allow_compact && cam.compact.col_guide8 && cam.compact.rel_column8;
         const size_t smem_k = compact ? (((size_t)cam.bokeh.h * 12u + 15u) & ~(size_t)15u) : smem;
-        const size_t need = (size_t)ZOICB_THIN_CTAS * (smem_k + 2200);
+        const int ctas = compact ? ZOICB_THIN_CTAS_COMPACT : ZOICB_THIN_CTAS;
+        const size_t need = (size_t)ctas * (smem_k + 2200);
         int pct = (int)((need * 100 + 233471) / 233472);
         if (carve >= 0) pct = carve;
         if (pct > 100) pct = 100;
         // (prepared blocks -- 32 samples made ready by one dense pass and parked in registers (call 16) or in L2 scratch
         // (call 21) for finished lanes to adopt -- save 6-12 % of the warp instructions, stay bit-exact and lose to the
         // registers / the L2 round trip they cost: profiles/r02_ab.txt)
-        const unsigned grid = (unsigned)sm_count() * ZOICB_THIN_CTAS;
+        const unsigned grid = (unsigned)sm_count() * (unsigned)ctas;
         if constexpr (kImage) {
             if (compact) {
                 cudaFuncSetAttribute(thin_persistent_kernel<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
