@@ -108,14 +108,15 @@ struct BokehView {
 };
 
 // kCompact: the byte-wide column tables (BokehCompact) and the rows' final CDF values from shared memory,
-// s_rows[2h + actual row] (staged by the caller, stage_row_finals): the same values from smaller / nearer places.
+// s_rows[h + actual row] (staged by the caller, stage_bokeh_compact): the same values from smaller / nearer places.
 template <bool kCompact = false>
 __device__ __forceinline__ void bokeh_sample(const BokehView& b, float u_row, float u_col, float* dx, float* dy) {
     // (a straight-line form of the row search for brackets of at most two entries, like the column search below, is no
     // faster: the row tables are in shared memory, there is no chain of long loads to shorten; profiles/r02_ab.txt call 26)
     int r = upper_bound_guided(b.h, b.row_shift, u_row, [&](int i) { return s_rows[i]; }, [&](int k) { return (int)__ldg(b.row_guide + k); });
     if (r >= b.h) r = b.h - 1;
-    const int row = __float_as_int(s_rows[b.h + r]);
+    // kCompact: rows as [CDF: h floats][final column-CDF value by actual row: h floats][row indices: h x 16 bit] (stage_bokeh_compact)
+    const int row = kCompact ? (int)reinterpret_cast<const uint16_t*>(s_rows + 2 * b.h)[r] : __float_as_int(s_rows[b.h + r]);
     const int start = row * b.w;
     const float* __restrict__ col = b.cdf_col + start;
     const int goff = row * ((1 << b.col_shift) + 2);
@@ -137,7 +138,7 @@ __device__ __forceinline__ void bokeh_sample(const BokehView& b, float u_row, fl
             const int k = f >= (float)G ? G : (int)f;
             first = (int)__ldg(cg + k);
             len = (int)__ldg(cg + k + 1) - first;
-            past = u_col >= s_rows[2 * b.h + row];
+            past = u_col >= s_rows[b.h + row];
         }
         const int maxlen = (int)__reduce_max_sync(__activemask(), (unsigned)len);
         if (maxlen <= 2) {
@@ -156,7 +157,7 @@ __device__ __forceinline__ void bokeh_sample(const BokehView& b, float u_row, fl
 #endif
         {
             c = upper_bound_guided(b.w, b.col_shift, u_col, [&](int i) { return __ldg(col + i); }, [&](int k) { return (int)__ldg(cg + k); },
-                                   [&]() { return s_rows[2 * b.h + row]; });
+                                   [&]() { return s_rows[b.h + row]; });
             if (c >= b.w) c = b.w - 1;
             rel = (int)__ldg(rl + c);
         }
@@ -206,12 +207,30 @@ __device__ __forceinline__ BokehView stage_bokeh(const CameraState& cam) {
     __syncthreads();
     return b;
 }
-// third row table of the kCompact callers: the final value of every row's column CDF, by actual row (the dynamic shared
-// memory must hold 12 bytes per row then: bokeh_smem_bytes(h) + 4 h)
-__device__ __forceinline__ void stage_row_finals(const CameraState& cam) {
-    const int w = cam.bokeh.w, h = cam.bokeh.h;
-    for (int i = threadIdx.x; i < h; i += blockDim.x) s_rows[2 * h + i] = cam.bokeh.cdf_column[(size_t)i * w + (w - 1)];
+// The row tables of the kCompact callers: [CDF: h floats][final value of every row's column CDF, by actual row: h floats]
+// [row indices: h x 16 bit] -- 10 bytes per row (compact_smem_bytes), so that eight CTAs' tables of a 255-row image
+// still fit the 32 KB carve-out.
+__host__ __device__ inline unsigned compact_smem_bytes(int h) { return ((unsigned)h * 10u + 15u) & ~15u; }
+__device__ __forceinline__ BokehView stage_bokeh_compact(const CameraState& cam) {
+    BokehView b;
+    b.w = cam.bokeh.w; b.h = cam.bokeh.h;
+    b.cdf_col = cam.bokeh.cdf_column;
+    b.rel_col = cam.bokeh.rel_column;
+    b.row_guide = cam.bokeh.row_guide;
+    b.col_guide = cam.bokeh.col_guide;
+    b.dx_of_col = cam.bokeh.dx_of_col;
+    b.dy_of_row = cam.bokeh.dy_of_row;
+    b.row_shift = cam.bokeh.row_shift; b.col_shift = cam.bokeh.col_shift;
+    b.col_guide8 = cam.compact.col_guide8;
+    b.rel_col8 = cam.compact.rel_column8;
+    uint16_t* idx16 = reinterpret_cast<uint16_t*>(s_rows + 2 * b.h);
+    for (int i = threadIdx.x; i < b.h; i += blockDim.x) {
+        s_rows[i] = cam.bokeh.cdf_row[i];
+        s_rows[b.h + i] = cam.bokeh.cdf_column[(size_t)i * b.w + (b.w - 1)];
+        idx16[i] = (uint16_t)cam.bokeh.row_indices[i];
+    }
     __syncthreads();
+    return b;
 }
 
 // ------------------------------------------------------------------------------------------------

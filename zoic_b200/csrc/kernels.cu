@@ -169,8 +169,7 @@ thin_persistent_kernel(const __grid_constant__ CameraState cam, const float4* __
                        uint64_t first_index, uint64_t seed, RayRecord* __restrict__ rays,
                        DeviceStats* stats, int stage_rows, unsigned long long* chunk_counter) {
     BokehView bk;
-    if (kImage) bk = stage_bokeh(cam);
-    if (kImage && kCompact) stage_row_finals(cam);
+    if (kImage) bk = kCompact ? stage_bokeh_compact(cam) : stage_bokeh(cam);
     (void)stage_rows;
     const ThinState& T = cam.thin;
     const unsigned lane = threadIdx.x & 31;
@@ -561,9 +560,9 @@ static cudaError_t launch_variant(const CameraState& cam, int mode, const float4
         // byte-wide column tables when the camera has them (ZOICB_THIN_COMPACT=0 turns them off: A/B)
         static const bool allow_compact = [] { const char* v = getenv("ZOICB_THIN_COMPACT"); return !v || atoi(v) != 0; }();
         const bool compact = kImage && allow_compact && cam.compact.col_guide8 && cam.compact.rel_column8;
-        const size_t smem_k = compact ? (((size_t)cam.bokeh.h * 12u + 15u) & ~(size_t)15u) : smem;
+        const size_t smem_k = compact ? compact_smem_bytes(cam.bokeh.h) : smem;
         const int ctas = compact ? ZOICB_THIN_CTAS_COMPACT : ZOICB_THIN_CTAS;
-        const size_t need = (size_t)ctas * (smem_k + 2200);
+        const size_t need = (size_t)ctas * (smem_k + (compact ? 1100 : 2200));   // + the 1 KB the system reserves per CTA and the counters
         int pct = (int)((need * 100 + 233471) / 233472);
         if (carve >= 0) pct = carve;
         if (pct > 100) pct = 100;
