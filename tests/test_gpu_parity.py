@@ -269,6 +269,40 @@ def test_guarded_kolb_no_lut_and_bokeh(port):
                         useImage=1, exposureControl=0.3), port, n=100_000, image=hex_bokeh_image(255))
 
 
+def test_thin_retry_kernel_on_random_images(port):
+    """The thin-lens retry kernel against the oracle on photograph-like aperture images: coarse value levels (ties, long
+    flat stretches of the CDFs -> search brackets far longer than the two entries the fast path handles), black rows and
+    columns, ragged sizes on both sides of the 255-column limit of the byte-wide tables, and lens samples at and beyond
+    the ends of [0, 1)."""
+    from zoic_b200 import ZoicCamera, MODE_GUARDED
+    rng = np.random.default_rng(77)
+    for w, h in [(255, 255), (200, 77), (33, 140), (7, 5), (255, 511), (256, 64), (300, 40)]:
+        levels = int(rng.choice([2, 5, 64]))
+        img = (rng.integers(0, levels, (h, w)).astype(np.float32) / np.float32(levels - 1)) ** 2
+        img[rng.integers(0, h, max(1, h // 8)), :] = 0.0          # black rows
+        img[:, rng.integers(0, w, max(1, w // 8))] = 0.0          # black columns
+        if img.sum() == 0:
+            img[h // 2, w // 2] = 1.0
+        image = np.ascontiguousarray(np.repeat(img[:, :, None], 3, axis=2))
+        kw = dict(lensModel=0, focalLength=3.5, fStop=2.0, useImage=1, opticalVignettingDistance=float(rng.uniform(1.0, 4.0)),
+                  opticalVignettingRadius=float(rng.uniform(0.7, 1.5)))
+        s = random_samples(40_000, seed=w * 1000 + h)
+        s[0, 2:] = [0.0, 0.0]
+        s[1, 2:] = [1.0, 1.0]
+        s[2, 2:] = [0.99999994, 0.5]
+        s[3, 2:] = [1.5, 0.25]
+        s[4, 2:] = [0.25, -0.25]
+        cam = ZoicCamera(image=image, **kw)
+        assert cam.mode == MODE_GUARDED
+        ref = port.PortCamera(image=image, **kw)
+        o, d, st = _run_gpu(cam, s, seed=3, first_index=11)
+        o2, d2, st2 = ref.generate(s, seed=3, first_index=11, nthreads=8)
+        assert bits_equal(o, o2) and bits_equal(d, d2), (w, h, levels)
+        assert st["attempts"] == st2["attempts"] and st["vignetted"] == st2["vignetted"], (w, h)
+        cam.close()
+        ref.close()
+
+
 def test_merged_normalisation_equals_the_ieee_operations_for_every_float():
     """The thin-lens retry kernel normalises with one range check around the fast paths of the IEEE root and the IEEE
     reciprocal (lens_math.cuh: normalize_factor).  The device compares it with __frcp_rn(__fsqrt_rn(x)) -- the reference's
